@@ -1,0 +1,169 @@
+/* klineprofiles_b200.h -- C ABI of the B200-native klineprofiles hot path.
+ *
+ * Drop-in boundary.  The five XSPEC model symbols at the bottom are exactly the symbols the
+ * reference exports (`pub export fn ... callconv(.c)`, reference src/xspec-wrapper.zig:425-530)
+ * and that xspec/lmodel.dat:1,9,23,30,43 binds as c_kline ... c_kconv10.  Everything prefixed
+ * klp_ is new: the reference evaluates one parameter set per call on one CPU thread; this
+ * library evaluates batches of independent parameter sets on one B200 per process.
+ *
+ * There is NO CPU fallback: every evaluation entry point returns KLP_ERR_CUDA (or, for the
+ * XSPEC symbols, logs and zero-fills like the reference does on error) when no CUDA device is
+ * usable.
+ */
+#ifndef KLINEPROFILES_B200_H
+#define KLINEPROFILES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* models: parameter layouts of reference xspec-wrapper.zig:209-322 / xspec/lmodel.dat */
+enum {
+    KLP_KLINE = 0,   /* {a, incl_deg, eline, rmin, rmax, alpha}                          6  */
+    KLP_KLINE5 = 1,  /* {a, incl_deg, eline, rmin, rmax, rcut, alpha, e1..e5}            12 */
+    KLP_KCONV = 2,   /* {a, incl_deg, rmin, rmax, alpha}                  (eline := 1)   5  */
+    KLP_KCONV5 = 3,  /* {a, incl_deg, rmin, rmax, rcut, alpha, e1..e5}    (eline := 1)   11 */
+    KLP_KCONV10 = 4  /* {a, incl_deg, rmin, rmax, rcut, alpha, e1..e10}   (eline := 1)   16 */
+};
+
+/* arithmetic type of the line-profile quadrature */
+enum {
+    KLP_F32 = 0, /* reference-faithful: f32 exactly as the reference instantiates it
+                    (LineProfileTable(2, f32), xspec-wrapper.zig:61,347-359), same operation order,
+                    no FMA contraction; rebin / normalise / convolution in f64 as in the reference */
+    KLP_F64 = 1  /* every f32 of the reference path replaced by f64 */
+};
+
+enum {
+    KLP_OK = 0,
+    KLP_ERR_ARG = 1,      /* bad argument */
+    KLP_ERR_CUDA = 2,     /* CUDA runtime failure / no device */
+    KLP_ERR_IO = 3,       /* table file missing or malformed */
+    KLP_ERR_NOMEM = 4
+};
+
+typedef struct klp_table klp_table; /* host + device copy of a transfer-function table, plus workspaces */
+
+/* Message of the last failing klp_* call on this thread. */
+const char* klp_last_error(void);
+
+/* Number of f64 parameters per set for a model (lmodel.dat), or -1. */
+int klp_model_nparams(int model);
+
+/* ---- transfer-function table (replaces reference io.readFitsFile, io.zig:53-87, and
+ *      LineProfileTable.init, line-profile.zig:233-273) ------------------------------------ */
+
+/* Build a table from host arrays and upload it to `device`.
+ *   spins[n_a], mus[n_mu] ascending (HDU2 / HDU3 of the reference FITS file; mus are cos(incl));
+ *   radii/gmin/gmax [n_a*n_mu][n_r] (radii descending within a frame);
+ *   upper/lower     [n_a*n_mu][n_r][n_g];
+ *   frame index = i_a * n_mu + i_mu (line-profile.zig:60-70).  n_g = 30 in the reference
+ *   (xspec-wrapper.zig:75); 2 <= n_g <= 64 here. */
+int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, int n_r, int n_g,
+                     const float* radii, const float* gmin, const float* gmax, const float* upper,
+                     const float* lower, int device, klp_table** out);
+
+/* Load a table file: the flat ".klpt" container written by lineprofiles_b200.tableio.save_table
+ * (see that file for the layout). */
+int klp_table_load(const char* path, int device, klp_table** out);
+
+void klp_table_destroy(klp_table* t);
+
+/* dims[4] = {n_a, n_mu, n_r, n_g} */
+int klp_table_dims(const klp_table* t, int* dims);
+
+/* Host-side index logic, mirrors of line-profile.zig:60-70, :72-93, :209-231, :196-207. */
+size_t klp_table_index(const klp_table* t, size_t i_a, size_t i_mu);
+void klp_find_parameter_indices(const klp_table* t, float a, float mu, size_t* out2);
+void klp_find_tables(const klp_table* t, const size_t* param_indices2, size_t* out4);
+int klp_parameter_weight(const klp_table* t, int which, float value, size_t index, float* weight); /* 0 => null */
+
+/* ---- batched evaluation (replaces kerr_lin_emisN / kerr_conv_emisN -> integrate_lineprofile /
+ *      kerr_convolve, xspec-wrapper.zig:134-205,326-421, for B independent parameter sets) ---- */
+
+/* Host buffers; the library stages through pinned memory, copies host->device, runs the kernels
+ * and copies the spectra back.  Every set is evaluated as a fresh process would (radial-grid
+ * limits [r_grid0[0], r_grid0[last]] of setup(), xspec-wrapper.zig:84,149-153).
+ *   params   [B][klp_model_nparams(model)] f64
+ *   energy   [n_flux+1] bin edges, keV, ascending (shared by all sets)
+ *   spectrum convolution models only: input spectrum, [n_flux] shared (spectrum_per_set = 0) or
+ *            [B][n_flux]; NULL for kline / kline5
+ *   out      [B][n_flux] f64 */
+int klp_eval_batch(klp_table* t, int model, int precision, long B, const double* params,
+                   const double* energy, int n_flux, const double* spectrum, int spectrum_per_set,
+                   double* out);
+
+/* Same, all pointers are device pointers on the table's device; work is enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised. */
+int klp_eval_batch_device(klp_table* t, int model, int precision, long B, const double* d_params,
+                          const double* d_energy, int n_flux, const double* d_spectrum,
+                          int spectrum_per_set, double* d_out, void* cuda_stream);
+
+/* Diagnostics for the parity tests: the fine-grid flux (1999 bins, before rebinning;
+ * flux_cache of xspec-wrapper.zig:64,156-160) widened to f64, and for convolution models the line
+ * profile on the fixed convolution grid (1998 bins, conv_flux of xspec-wrapper.zig:68,197).
+ * Either output pointer may be NULL.  Host buffers. */
+int klp_eval_debug(klp_table* t, int model, int precision, long B, const double* params,
+                   const double* energy, int n_flux, double* fine_out /*[B][1999]*/,
+                   double* profile_out /*[B][1998]*/);
+
+/* Stand-alone frame blend (LineProfileTable.interpolate_parameters, line-profile.zig:116-176):
+ * for each set (a, incl_deg) writes the blended frame as T = f32/f64, layout
+ * radii[n_r] gmin[n_r] gmax[n_r] upper[n_r][n_g] lower[n_r][n_g].  Device pointers.
+ * a_incl: [B][2] f64.  out: [B][n_r*(2*n_g+3)] T. */
+int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d_a_incl, void* d_out,
+                            void* cuda_stream);
+
+/* Per-kernel device time of the most recent klp_eval_batch_device call when timing is enabled
+ * (klp_set_timing(t, 1)): ms[0] setup, ms[1] quadrature, ms[2] rebin, ms[3] convolution;
+ * launches[4] likewise.  Enabling timing adds cudaEvent records on the caller's stream. */
+int klp_set_timing(klp_table* t, int enable);
+int klp_get_timing(klp_table* t, double* ms4, long* launches4);
+
+/* Tuning knobs (testing / benchmarking): "quad_threads" (128..1024), "splits" (CTAs per set,
+ * 0 = auto), "chunk" (sets per internal chunk). */
+int klp_set_option(klp_table* t, const char* key, long value);
+
+/* Peak-rate microbenchmark on the table's device: dependent-chain-free FMA throughput in
+ * GFLOP/s for precision f32 / f64 (denominator of the compute roofline). */
+int klp_fma_peak_gflops(klp_table* t, int precision, double* gflops);
+
+/* ---- the XSPEC model surface (reference xspec-wrapper.zig:425-530) -------------------------
+ * void f(const double* energy   n_flux+1 bin edges,
+ *        int n_flux,
+ *        const double* params   layout per model (above),
+ *        int spectrum           unused,
+ *        double* flux           additive: output; convolution: input spectrum in, result out,
+ *        double* flux_variance  unused, never touched,
+ *        const char* init       unused)
+ * Process-global state like the reference (xspec-wrapper.zig:57-68): on first use the table is
+ * loaded from $KLINE_PROF_DATA_DIR (default ".") -- "kerr-transfer-functions.klpt" -- or from the
+ * table installed with klp_set_default_table().  Errors: message on stderr prefixed
+ * "kerrlineprofile: ", "MODEL OUTPUT SET TO ZERO", flux zero-filled (xspec-wrapper.zig:361-372).
+ * The radial-grid limit ratchet of the reference (limits only shrink across calls,
+ * xspec-wrapper.zig:149-153) is reproduced; klp_legacy_reset() restores a fresh process. */
+void kline(const double* energy, int n_flux, const double* params, int spectrum, double* flux,
+           double* flux_variance, const char* init);
+void kline5(const double* energy, int n_flux, const double* params, int spectrum, double* flux,
+            double* flux_variance, const char* init);
+void kconv(const double* energy, int n_flux, const double* params, int spectrum, double* flux,
+           double* flux_variance, const char* init);
+void kconv5(const double* energy, int n_flux, const double* params, int spectrum, double* flux,
+            double* flux_variance, const char* init);
+void kconv10(const double* energy, int n_flux, const double* params, int spectrum, double* flux,
+             double* flux_variance, const char* init);
+
+/* Install `t` (not owned) as the table used by the XSPEC symbols; NULL uninstalls. */
+void klp_set_default_table(klp_table* t);
+/* Precision used by the XSPEC symbols (default KLP_F32, the reference's). */
+void klp_set_legacy_precision(int precision);
+/* Forget the radial-limit ratchet (as if the process had just started). */
+void klp_legacy_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLINEPROFILES_B200_H */

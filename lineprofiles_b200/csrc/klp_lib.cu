@@ -1,0 +1,850 @@
+// klp_lib.cu -- host side of the C ABI declared in include/klineprofiles_b200.h.
+//
+// Mirrors the reference's src/xspec-wrapper.zig for the hot path: model dispatch
+// (kerr_lin_emisN / kerr_conv_emisN, :326-421), process-global state of the XSPEC symbols
+// (:57-68), table lookup by $KLINE_PROF_DATA_DIR (:30-48), log-and-zero error convention
+// (:361-372) -- and adds the batched engine on top (chunking, pinned staging, stream overlap).
+// No CPU compute path exists in this file: every evaluation launches the kernels of
+// klp_kernels.cuh or fails.
+#include "../../include/klineprofiles_b200.h"
+#include "klp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace klp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define KLP_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(KLP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+int model_nparams(int model) {
+    switch (model) {
+        case KLP_KLINE: return 6;
+        case KLP_KLINE5: return 12;
+        case KLP_KCONV: return 5;
+        case KLP_KCONV5: return 11;
+        case KLP_KCONV10: return 16;
+    }
+    return -1;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KLP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(KLP_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = bytes;
+        return KLP_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KLP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) return fail(KLP_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        cap = bytes;
+        return KLP_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct EvalExtra {
+    bool use_limits = false;
+    double lim_lo = 0, lim_hi = 0;
+    bool want_lims = false;  // write new end points of set 0 into table->d_lims
+};
+
+}  // namespace
+
+struct klp_table {
+    int device = 0;
+    int n_a = 0, n_mu = 0, n_r = 0, n_g = 0;
+    size_t frame_stride = 0;
+    std::vector<float> spins, mus;
+    float* d_frames = nullptr;
+    float* d_spins = nullptr;
+    float* d_mus = nullptr;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // workspaces
+    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims;
+    // host-API staging
+    Buf d_energy, d_spec, d_params[2], d_out[2], d_spec_slot[2];
+    PinBuf h_params[2], h_out[2], h_spec_slot[2];
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    // options
+    int quad_threads = 0;  // 0 = auto
+    int splits = 0;        // 0 = auto
+    long chunk = 16384;
+    // timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (kind, pool index)
+    size_t ev_next = 0;
+    double ms[4] = {0, 0, 0, 0};
+    long launches[4] = {0, 0, 0, 0};
+    std::mutex mu_;
+};
+
+namespace {
+
+// ---- timing helpers ------------------------------------------------------------------------
+struct TimedLaunch {
+    klp_table* t;
+    cudaStream_t st;
+    int kind;
+    int idx = -1;
+    TimedLaunch(klp_table* t_, cudaStream_t st_, int kind_) : t(t_), st(st_), kind(kind_) {
+        if (!t->timing) return;
+        if (t->ev_next == t->ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            t->ev_pool.push_back({a, b});
+        }
+        idx = (int)t->ev_next++;
+        cudaEventRecord(t->ev_pool[idx].first, st);
+    }
+    ~TimedLaunch() {
+        if (idx < 0) return;
+        cudaEventRecord(t->ev_pool[idx].second, st);
+        t->ev_used.push_back({kind, idx});
+    }
+};
+
+template <class T> CallConsts<T>* cc_ptr(klp_table* t);
+template <> CallConsts<float>* cc_ptr<float>(klp_table* t) { return (CallConsts<float>*)t->cc32.p; }
+template <> CallConsts<double>* cc_ptr<double>(klp_table* t) { return (CallConsts<double>*)t->cc64.p; }
+
+template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, int& grid_out, cudaStream_t st, bool dry) {
+    const int NW = NT / 32;
+    size_t fixed = QuadSmem<T>::fixed_bytes(t->n_g, NW);
+    size_t fb = QuadSmem<T>::frame_bytes(t->n_r, t->n_g);
+    bool in_smem = fixed + fb <= (size_t)t->max_smem_optin;
+    size_t smem = fixed + (in_smem ? fb : 0);
+    if (smem > (size_t)t->max_smem_optin) return fail(KLP_ERR_ARG, "table rows too wide for shared memory");
+    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT>, NT, smem));
+    if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
+    const long long resident = (long long)occ * t->sm_count;
+    int splits = t->splits;
+    if (splits <= 0) {
+        splits = 1;
+        if (q.B < resident) splits = (int)std::min<long long>(kNGroups, (resident + q.B - 1) / q.B);
+    }
+    splits = std::max(1, std::min(splits, kNGroups));
+    q.splits = splits;
+    const long long items = q.B * splits;
+    int grid = (int)std::min<long long>(items, resident);
+    grid_out = grid;
+    q.frame_in_smem = in_smem ? 1 : 0;
+    if (!in_smem) {
+        int rc = t->scratch.ensure((size_t)grid * fb);
+        if (rc) return rc;
+        q.scratch = (T*)t->scratch.p;
+    }
+    if (dry) return KLP_OK;
+    k_quad<T, NT><<<grid, NT, smem, st>>>(q);
+    KLP_CUDA(cudaGetLastError());
+    return KLP_OK;
+}
+
+template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
+    int nt = t->quad_threads;
+    if (nt <= 0) nt = sizeof(T) == 4 ? 256 : 512;
+    int grid = 0;
+    switch (nt) {
+        case 128: return launch_quad_nt<T, 128>(t, q, grid, st, false);
+        case 256: return launch_quad_nt<T, 256>(t, q, grid, st, false);
+        case 512: return launch_quad_nt<T, 512>(t, q, grid, st, false);
+        case 1024: return launch_quad_nt<T, 1024>(t, q, grid, st, false);
+    }
+    return fail(KLP_ERR_ARG, "quad_threads must be 128, 256, 512 or 1024");
+}
+
+TableDev table_dev(const klp_table* t) {
+    TableDev d;
+    d.frames = t->d_frames;
+    d.spins = t->d_spins;
+    d.mus = t->d_mus;
+    d.frame_stride = t->frame_stride;
+    d.n_a = t->n_a;
+    d.n_mu = t->n_mu;
+    d.n_r = t->n_r;
+    d.n_g = t->n_g;
+    return d;
+}
+
+// One batch on one stream, device pointers.  fine_keep / prof_keep: debug taps (device pointers to
+// [B][kFineG] T and [B][kConvN-1] f64) -- when given, B must fit one chunk.
+template <class T>
+int eval_device_t(klp_table* t, int model, long long B, const double* d_params, const double* d_energy, int n_flux,
+                  const double* d_spec, int per_set, double* d_out, cudaStream_t st, const EvalExtra& ex,
+                  bool stop_after_profile) {
+    const int P = model_nparams(model);
+    const bool conv = model >= 2;
+    Buf& ccb = sizeof(T) == 4 ? t->cc32 : t->cc64;
+    int rc;
+    if ((rc = ccb.ensure(sizeof(CallConsts<T>)))) return rc;
+    if ((rc = t->counter.ensure(sizeof(unsigned long long) * 4096))) return rc;
+    if ((rc = t->lims.ensure(sizeof(double) * 2))) return rc;
+    if (conv) {
+        if ((rc = t->conv_grid.ensure(sizeof(double) * kConvN))) return rc;
+        if ((rc = t->conv_avg.ensure(sizeof(double) * (size_t)n_flux))) return rc;
+    }
+    const long long chunk = std::max<long long>(1, std::min<long long>(t->chunk, B));
+    if ((rc = t->fine.ensure(sizeof(T) * (size_t)chunk * kFineG))) return rc;
+    if (conv && (rc = t->prof.ensure(sizeof(double) * (size_t)chunk * (kConvN - 1)))) return rc;
+
+    {
+        TimedLaunch tl(t, st, 0);
+        SetupArgs sa;
+        sa.energy = d_energy;
+        sa.n_flux = n_flux;
+        sa.n_g = t->n_g;
+        sa.is_conv = conv ? 1 : 0;
+        sa.conv_grid = (double*)t->conv_grid.p;
+        sa.conv_avg = (double*)t->conv_avg.p;
+        k_setup<T><<<1, 128, 0, st>>>(sa, cc_ptr<T>(t));
+        KLP_CUDA(cudaGetLastError());
+    }
+    const long long n_chunks = (B + chunk - 1) / chunk;
+    if (n_chunks > 4096) return fail(KLP_ERR_ARG, "batch too large for the chunk size");
+    KLP_CUDA(cudaMemsetAsync(t->counter.p, 0, sizeof(unsigned long long) * (size_t)n_chunks, st));
+    for (long long c = 0; c < n_chunks; ++c) {
+        const long long off = c * chunk;
+        const long long nb = std::min(chunk, B - off);
+        QuadArgs<T> q;
+        q.tab = table_dev(t);
+        q.cc = cc_ptr<T>(t);
+        q.params = d_params + (size_t)off * P;
+        q.model = model;
+        q.P = P;
+        q.B = nb;
+        q.splits = 1;
+        q.fine = (T*)t->fine.p;
+        q.scratch = nullptr;
+        q.frame_in_smem = 1;
+        q.counter = (unsigned long long*)t->counter.p + c;
+        q.use_limits = ex.use_limits ? 1 : 0;
+        q.lim_lo = (T)ex.lim_lo;
+        q.lim_hi = (T)ex.lim_hi;
+        q.lims_out = (ex.want_lims && c == 0) ? (T*)t->lims.p : nullptr;
+        {
+            TimedLaunch tl(t, st, 1);
+            if ((rc = launch_quad<T>(t, q, st))) return rc;
+        }
+        {
+            TimedLaunch tl(t, st, 2);
+            RebinArgs<T> r;
+            r.cc = cc_ptr<T>(t);
+            r.params = q.params;
+            r.model = model;
+            r.P = P;
+            r.B = nb;
+            r.fine = (const T*)t->fine.p;
+            if (conv) {
+                r.energy = (const double*)t->conv_grid.p;
+                r.n_out = kConvN - 1;
+                r.out = (double*)t->prof.p;
+                r.out_stride = kConvN - 1;
+            } else {
+                r.energy = d_energy;
+                r.n_out = n_flux;
+                r.out = d_out + (size_t)off * n_flux;
+                r.out_stride = (size_t)n_flux;
+            }
+            k_rebin<T><<<(unsigned)nb, 128, 0, st>>>(r);
+            KLP_CUDA(cudaGetLastError());
+        }
+        if (conv && !stop_after_profile) {
+            TimedLaunch tl(t, st, 3);
+            ConvArgs ca;
+            ca.g = (const double*)t->conv_grid.p;
+            ca.prof = (const double*)t->prof.p;
+            ca.prof_stride = kConvN - 1;
+            ca.x = d_energy;
+            ca.avg = (const double*)t->conv_avg.p;
+            ca.spec = per_set ? d_spec + (size_t)off * n_flux : d_spec;
+            ca.per_set = per_set;
+            ca.n = n_flux;
+            ca.out = d_out + (size_t)off * n_flux;
+            dim3 grid((unsigned)((n_flux + kConvThreads - 1) / kConvThreads), (unsigned)nb);
+            // gridDim.y limit is 65535
+            if (nb > 65535) return fail(KLP_ERR_ARG, "chunk must be <= 65535 for convolution models");
+            k_conv<<<grid, kConvThreads, 0, st>>>(ca);
+            KLP_CUDA(cudaGetLastError());
+        }
+    }
+    return KLP_OK;
+}
+
+int eval_device(klp_table* t, int model, int precision, long long B, const double* d_params, const double* d_energy,
+                int n_flux, const double* d_spec, int per_set, double* d_out, cudaStream_t st, const EvalExtra& ex,
+                bool stop_after_profile = false) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    if (model_nparams(model) < 0) return fail(KLP_ERR_ARG, "unknown model");
+    if (precision != KLP_F32 && precision != KLP_F64) return fail(KLP_ERR_ARG, "unknown precision");
+    if (B < 0 || n_flux < 1) return fail(KLP_ERR_ARG, "bad batch or grid size");
+    if (B == 0) return KLP_OK;
+    if (!d_params || !d_energy || (!d_out && !stop_after_profile)) return fail(KLP_ERR_ARG, "null buffer");
+    if (model >= 2 && !d_spec && !stop_after_profile) return fail(KLP_ERR_ARG, "convolution models need an input spectrum");
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (t->timing) { t->ev_next = 0; t->ev_used.clear(); }
+    if (precision == KLP_F32)
+        return eval_device_t<float>(t, model, B, d_params, d_energy, n_flux, d_spec, per_set, d_out, st, ex, stop_after_profile);
+    return eval_device_t<double>(t, model, B, d_params, d_energy, n_flux, d_spec, per_set, d_out, st, ex, stop_after_profile);
+}
+
+int ensure_streams(klp_table* t) {
+    if (t->s_compute) return KLP_OK;
+    KLP_CUDA(cudaStreamCreateWithFlags(&t->s_compute, cudaStreamNonBlocking));
+    KLP_CUDA(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
+    KLP_CUDA(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        KLP_CUDA(cudaEventCreateWithFlags(&t->ev_h2d[k], cudaEventDisableTiming));
+        KLP_CUDA(cudaEventCreateWithFlags(&t->ev_comp[k], cudaEventDisableTiming));
+        KLP_CUDA(cudaEventCreateWithFlags(&t->ev_d2h[k], cudaEventDisableTiming));
+    }
+    return KLP_OK;
+}
+
+// Host-buffer batch: chunked, double-buffered through pinned memory; H2D, compute and D2H run on
+// three streams so copies overlap the kernels.
+int eval_host(klp_table* t, int model, int precision, long long B, const double* params, const double* energy,
+              int n_flux, const double* spectrum, int per_set, double* out, const EvalExtra& ex, double* lims_out) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    const int P = model_nparams(model);
+    if (P < 0) return fail(KLP_ERR_ARG, "unknown model");
+    if (B < 0 || n_flux < 1) return fail(KLP_ERR_ARG, "bad batch or grid size");
+    if (B == 0) return KLP_OK;
+    if (!params || !energy || !out) return fail(KLP_ERR_ARG, "null buffer");
+    const bool conv = model >= 2;
+    if (conv && !spectrum) return fail(KLP_ERR_ARG, "convolution models need an input spectrum");
+    for (int i = 0; i < n_flux; ++i)
+        if (!(energy[i + 1] > energy[i])) return fail(KLP_ERR_ARG, "energy edges must be strictly ascending");
+    std::lock_guard<std::mutex> lk(t->mu_);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    int rc;
+    if ((rc = ensure_streams(t))) return rc;
+    if ((rc = t->d_energy.ensure(sizeof(double) * (size_t)(n_flux + 1)))) return rc;
+    KLP_CUDA(cudaMemcpyAsync(t->d_energy.p, energy, sizeof(double) * (size_t)(n_flux + 1), cudaMemcpyHostToDevice, t->s_compute));
+    if (conv && !per_set) {
+        if ((rc = t->d_spec.ensure(sizeof(double) * (size_t)n_flux))) return rc;
+        KLP_CUDA(cudaMemcpyAsync(t->d_spec.p, spectrum, sizeof(double) * (size_t)n_flux, cudaMemcpyHostToDevice, t->s_compute));
+    }
+    KLP_CUDA(cudaStreamSynchronize(t->s_compute));
+    // staging chunk: ~64 MB of output per slot
+    long long hc = (64ll << 20) / ((long long)n_flux * 8);
+    hc = std::max<long long>(256, std::min<long long>(hc, 16384));
+    hc = std::min(hc, B);
+    const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux;
+    const size_t par_bytes = sizeof(double) * (size_t)hc * P;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = t->d_params[k].ensure(par_bytes)) || (rc = t->d_out[k].ensure(out_bytes)) ||
+            (rc = t->h_params[k].ensure(par_bytes)) || (rc = t->h_out[k].ensure(out_bytes)))
+            return rc;
+        if (conv && per_set)
+            if ((rc = t->d_spec_slot[k].ensure(out_bytes)) || (rc = t->h_spec_slot[k].ensure(out_bytes))) return rc;
+    }
+    const long long n_chunks = (B + hc - 1) / hc;
+    long long pending_off[2] = {-1, -1}, pending_n[2] = {0, 0};
+    auto drain = [&](int k) -> int {
+        if (pending_off[k] < 0) return KLP_OK;
+        KLP_CUDA(cudaEventSynchronize(t->ev_d2h[k]));
+        std::memcpy(out + (size_t)pending_off[k] * n_flux, t->h_out[k].p, sizeof(double) * (size_t)pending_n[k] * n_flux);
+        pending_off[k] = -1;
+        return KLP_OK;
+    };
+    const bool saved_timing = t->timing;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const int k = (int)(c & 1);
+        const long long off = c * hc, nb = std::min(hc, B - off);
+        if ((rc = drain(k))) return rc;
+        std::memcpy(t->h_params[k].p, params + (size_t)off * P, sizeof(double) * (size_t)nb * P);
+        KLP_CUDA(cudaMemcpyAsync(t->d_params[k].p, t->h_params[k].p, sizeof(double) * (size_t)nb * P, cudaMemcpyHostToDevice, t->s_h2d));
+        const double* dspec = (const double*)t->d_spec.p;
+        if (conv && per_set) {
+            std::memcpy(t->h_spec_slot[k].p, spectrum + (size_t)off * n_flux, sizeof(double) * (size_t)nb * n_flux);
+            KLP_CUDA(cudaMemcpyAsync(t->d_spec_slot[k].p, t->h_spec_slot[k].p, sizeof(double) * (size_t)nb * n_flux, cudaMemcpyHostToDevice, t->s_h2d));
+            dspec = (const double*)t->d_spec_slot[k].p;
+        }
+        KLP_CUDA(cudaEventRecord(t->ev_h2d[k], t->s_h2d));
+        KLP_CUDA(cudaStreamWaitEvent(t->s_compute, t->ev_h2d[k], 0));
+        EvalExtra e2 = ex;
+        e2.want_lims = ex.want_lims && c == 0;
+        if (c > 0) t->timing = false;  // per-kernel timing covers the first staging chunk only
+        rc = eval_device(t, model, precision, nb, (const double*)t->d_params[k].p, (const double*)t->d_energy.p, n_flux,
+                         dspec, per_set, (double*)t->d_out[k].p, t->s_compute, e2);
+        t->timing = saved_timing;
+        if (rc) return rc;
+        KLP_CUDA(cudaEventRecord(t->ev_comp[k], t->s_compute));
+        KLP_CUDA(cudaStreamWaitEvent(t->s_d2h, t->ev_comp[k], 0));
+        KLP_CUDA(cudaMemcpyAsync(t->h_out[k].p, t->d_out[k].p, sizeof(double) * (size_t)nb * n_flux, cudaMemcpyDeviceToHost, t->s_d2h));
+        KLP_CUDA(cudaEventRecord(t->ev_d2h[k], t->s_d2h));
+        pending_off[k] = off;
+        pending_n[k] = nb;
+    }
+    if ((rc = drain(0)) || (rc = drain(1))) return rc;
+    if (lims_out && ex.want_lims) {
+        if (precision == KLP_F32) {
+            float l[2];
+            KLP_CUDA(cudaMemcpy(l, t->lims.p, sizeof(l), cudaMemcpyDeviceToHost));
+            lims_out[0] = l[0];
+            lims_out[1] = l[1];
+        } else {
+            KLP_CUDA(cudaMemcpy(lims_out, t->lims.p, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+        }
+    }
+    KLP_CUDA(cudaGetLastError());
+    return KLP_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* klp_last_error(void) { return g_err.c_str(); }
+
+int klp_model_nparams(int model) { return model_nparams(model); }
+
+int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, int n_r, int n_g, const float* radii,
+                     const float* gmin, const float* gmax, const float* upper, const float* lower, int device,
+                     klp_table** out) {
+    if (!out) return fail(KLP_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!spins || !mus || !radii || !gmin || !gmax || !upper || !lower) return fail(KLP_ERR_ARG, "null table array");
+    if (n_a < 1 || n_mu < 1 || n_r < 3 || n_g < 2 || n_g > kMaxNG) return fail(KLP_ERR_ARG, "bad table dimensions");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(KLP_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(KLP_ERR_ARG, "bad device ordinal");
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select CUDA device");
+    klp_table* t = new klp_table;
+    t->device = device;
+    t->n_a = n_a; t->n_mu = n_mu; t->n_r = n_r; t->n_g = n_g;
+    t->spins.assign(spins, spins + n_a);
+    t->mus.assign(mus, mus + n_mu);
+    const size_t frame_len = (size_t)n_r * (2 * n_g + 3);
+    t->frame_stride = (frame_len + 3) & ~(size_t)3;
+    const size_t F = (size_t)n_a * n_mu;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete t; return fail(KLP_ERR_CUDA, "cudaGetDeviceProperties"); }
+    t->sm_count = prop.multiProcessorCount;
+    t->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    auto bail = [&](int code, const std::string& m) { klp_table_destroy(t); return fail(code, m); };
+    if (cudaMalloc(&t->d_frames, sizeof(float) * F * t->frame_stride) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(frames)");
+    if (cudaMalloc(&t->d_spins, sizeof(float) * n_a) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(spins)");
+    if (cudaMalloc(&t->d_mus, sizeof(float) * n_mu) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(mus)");
+    // pack frames: radii | gmin | gmax | upper | lower, padded to the stride; staged in slabs
+    const size_t slab_frames = std::max<size_t>(1, (64u << 20) / (sizeof(float) * t->frame_stride));
+    std::vector<float> slab(slab_frames * t->frame_stride, 0.f);
+    for (size_t f0 = 0; f0 < F; f0 += slab_frames) {
+        const size_t nf = std::min(slab_frames, F - f0);
+        for (size_t k = 0; k < nf; ++k) {
+            const size_t f = f0 + k;
+            float* dst = slab.data() + k * t->frame_stride;
+            std::memcpy(dst, radii + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + n_r, gmin + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + 2 * (size_t)n_r, gmax + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + 3 * (size_t)n_r, upper + f * (size_t)n_r * n_g, sizeof(float) * (size_t)n_r * n_g);
+            std::memcpy(dst + 3 * (size_t)n_r + (size_t)n_r * n_g, lower + f * (size_t)n_r * n_g, sizeof(float) * (size_t)n_r * n_g);
+        }
+        if (cudaMemcpy(t->d_frames + f0 * t->frame_stride, slab.data(), sizeof(float) * nf * t->frame_stride,
+                       cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(KLP_ERR_CUDA, "cudaMemcpy(frames)");
+    }
+    if (cudaMemcpy(t->d_spins, spins, sizeof(float) * n_a, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t->d_mus, mus, sizeof(float) * n_mu, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(KLP_ERR_CUDA, "cudaMemcpy(parameters)");
+    *out = t;
+    return KLP_OK;
+}
+
+int klp_table_load(const char* path, int device, klp_table** out) {
+    if (!out) return fail(KLP_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!path) return fail(KLP_ERR_ARG, "null path");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(KLP_ERR_IO, std::string("cannot open table file: ") + path);
+    char magic[8];
+    int32_t d[4];
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "KLPT0001", 8) != 0 || std::fread(d, 4, 4, f) != 4) {
+        std::fclose(f);
+        return fail(KLP_ERR_IO, std::string("not a KLPT0001 table: ") + path);
+    }
+    const int n_a = d[0], n_mu = d[1], n_r = d[2], n_g = d[3];
+    if (n_a < 1 || n_mu < 1 || n_r < 3 || n_g < 2 || n_g > kMaxNG) { std::fclose(f); return fail(KLP_ERR_IO, "bad table dimensions in file"); }
+    const size_t F = (size_t)n_a * n_mu, per = (size_t)n_r * (2 * n_g + 3);
+    std::vector<float> spins(n_a), mus(n_mu), body(F * per);
+    bool ok = std::fread(spins.data(), 4, n_a, f) == (size_t)n_a && std::fread(mus.data(), 4, n_mu, f) == (size_t)n_mu &&
+              std::fread(body.data(), 4, F * per, f) == F * per;
+    std::fclose(f);
+    if (!ok) return fail(KLP_ERR_IO, std::string("truncated table file: ") + path);
+    std::vector<float> radii(F * n_r), gmin(F * n_r), gmax(F * n_r), upper(F * (size_t)n_r * n_g), lower(F * (size_t)n_r * n_g);
+    for (size_t fr = 0; fr < F; ++fr) {
+        const float* src = body.data() + fr * per;
+        std::memcpy(&radii[fr * n_r], src, 4 * (size_t)n_r);
+        std::memcpy(&gmin[fr * n_r], src + n_r, 4 * (size_t)n_r);
+        std::memcpy(&gmax[fr * n_r], src + 2 * (size_t)n_r, 4 * (size_t)n_r);
+        std::memcpy(&upper[fr * (size_t)n_r * n_g], src + 3 * (size_t)n_r, 4 * (size_t)n_r * n_g);
+        std::memcpy(&lower[fr * (size_t)n_r * n_g], src + 3 * (size_t)n_r + (size_t)n_r * n_g, 4 * (size_t)n_r * n_g);
+    }
+    return klp_table_create(spins.data(), n_a, mus.data(), n_mu, n_r, n_g, radii.data(), gmin.data(), gmax.data(),
+                            upper.data(), lower.data(), device, out);
+}
+
+void klp_table_destroy(klp_table* t) {
+    if (!t) return;
+    {
+        DeviceGuard dg(t->device);
+        cudaDeviceSynchronize();
+        if (t->d_frames) cudaFree(t->d_frames);
+        if (t->d_spins) cudaFree(t->d_spins);
+        if (t->d_mus) cudaFree(t->d_mus);
+        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims,
+                       &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
+                       &t->d_spec_slot[0], &t->d_spec_slot[1]})
+            b->release();
+        for (PinBuf* b : {&t->h_params[0], &t->h_params[1], &t->h_out[0], &t->h_out[1], &t->h_spec_slot[0], &t->h_spec_slot[1]})
+            b->release();
+        if (t->s_compute) cudaStreamDestroy(t->s_compute);
+        if (t->s_h2d) cudaStreamDestroy(t->s_h2d);
+        if (t->s_d2h) cudaStreamDestroy(t->s_d2h);
+        for (int k = 0; k < 2; ++k) {
+            if (t->ev_h2d[k]) cudaEventDestroy(t->ev_h2d[k]);
+            if (t->ev_comp[k]) cudaEventDestroy(t->ev_comp[k]);
+            if (t->ev_d2h[k]) cudaEventDestroy(t->ev_d2h[k]);
+        }
+        for (auto& p : t->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    }
+    delete t;
+}
+
+int klp_table_dims(const klp_table* t, int* dims) {
+    if (!t || !dims) return fail(KLP_ERR_ARG, "null argument");
+    dims[0] = t->n_a; dims[1] = t->n_mu; dims[2] = t->n_r; dims[3] = t->n_g;
+    return KLP_OK;
+}
+
+// line-profile.zig:60-70
+size_t klp_table_index(const klp_table* t, size_t i_a, size_t i_mu) { return i_a * (size_t)t->n_mu + i_mu; }
+
+// line-profile.zig:72-93 (first >=, none -> 0)
+void klp_find_parameter_indices(const klp_table* t, float a, float mu, size_t* out2) {
+    out2[0] = 0;
+    out2[1] = 0;
+    for (size_t i = 0; i < t->spins.size(); ++i) if (t->spins[i] >= a) { out2[0] = i; break; }
+    for (size_t i = 0; i < t->mus.size(); ++i) if (t->mus[i] >= mu) { out2[1] = i; break; }
+}
+
+// line-profile.zig:209-231
+void klp_find_tables(const klp_table* t, const size_t* pi, size_t* out4) {
+    size_t p0 = pi[0], p1 = pi[1];
+    out4[1] = klp_table_index(t, p0, p1);
+    if (p0 > 0) p0 -= 1;
+    out4[0] = klp_table_index(t, p0, p1);
+    if (p1 > 0) p1 -= 1;
+    out4[2] = klp_table_index(t, p0, p1);
+    if (p0 < pi[0]) p0 += 1;
+    out4[3] = klp_table_index(t, p0, p1);
+}
+
+// line-profile.zig:196-207
+int klp_parameter_weight(const klp_table* t, int which, float value, size_t index, float* weight) {
+    if (index == 0) return 0;
+    const std::vector<float>& arr = which == 0 ? t->spins : t->mus;
+    if (index >= arr.size()) return 0;
+    *weight = (value - arr[index - 1]) / (arr[index] - arr[index - 1]);
+    return 1;
+}
+
+int klp_eval_batch_device(klp_table* t, int model, int precision, long B, const double* d_params, const double* d_energy,
+                          int n_flux, const double* d_spectrum, int spectrum_per_set, double* d_out, void* cuda_stream) {
+    EvalExtra ex;
+    return eval_device(t, model, precision, B, d_params, d_energy, n_flux, d_spectrum, spectrum_per_set, d_out,
+                       (cudaStream_t)cuda_stream, ex);
+}
+
+int klp_eval_batch(klp_table* t, int model, int precision, long B, const double* params, const double* energy, int n_flux,
+                   const double* spectrum, int spectrum_per_set, double* out) {
+    EvalExtra ex;
+    return eval_host(t, model, precision, B, params, energy, n_flux, spectrum, spectrum_per_set, out, ex, nullptr);
+}
+
+int klp_eval_debug(klp_table* t, int model, int precision, long B, const double* params, const double* energy, int n_flux,
+                   double* fine_out, double* profile_out) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    const int P = model_nparams(model);
+    if (P < 0 || B < 1 || n_flux < 1 || !params || !energy) return fail(KLP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(t->mu_);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (B > t->chunk) return fail(KLP_ERR_ARG, "klp_eval_debug: B must fit one chunk");
+    int rc;
+    if ((rc = ensure_streams(t))) return rc;
+    Buf dpar, den, dout;
+    auto cleanup = [&]() { dpar.release(); den.release(); dout.release(); };
+    if ((rc = dpar.ensure(sizeof(double) * (size_t)B * P)) || (rc = den.ensure(sizeof(double) * (size_t)(n_flux + 1))) ||
+        (rc = dout.ensure(sizeof(double) * (size_t)B * n_flux))) { cleanup(); return rc; }
+    cudaMemcpy(dpar.p, params, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice);
+    cudaMemcpy(den.p, energy, sizeof(double) * (size_t)(n_flux + 1), cudaMemcpyHostToDevice);
+    EvalExtra ex;
+    rc = eval_device(t, model, precision, B, (const double*)dpar.p, (const double*)den.p, n_flux, nullptr, 0, (double*)dout.p,
+                     t->s_compute, ex, /*stop_after_profile=*/true);
+    if (rc) { cleanup(); return rc; }
+    cudaError_t e = cudaStreamSynchronize(t->s_compute);
+    if (e != cudaSuccess) { cleanup(); return fail(KLP_ERR_CUDA, std::string("kernel failed: ") + cudaGetErrorString(e)); }
+    if (fine_out) {
+        if (precision == KLP_F32) {
+            std::vector<float> h((size_t)B * kFineG);
+            cudaMemcpy(h.data(), t->fine.p, sizeof(float) * h.size(), cudaMemcpyDeviceToHost);
+            for (long s = 0; s < B; ++s)
+                for (int i = 0; i < kNFine; ++i) fine_out[(size_t)s * kNFine + i] = h[(size_t)s * kFineG + i];
+        } else {
+            std::vector<double> h((size_t)B * kFineG);
+            cudaMemcpy(h.data(), t->fine.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost);
+            for (long s = 0; s < B; ++s)
+                for (int i = 0; i < kNFine; ++i) fine_out[(size_t)s * kNFine + i] = h[(size_t)s * kFineG + i];
+        }
+    }
+    if (profile_out && model >= 2)
+        cudaMemcpy(profile_out, t->prof.p, sizeof(double) * (size_t)B * (kConvN - 1), cudaMemcpyDeviceToHost);
+    cleanup();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(KLP_ERR_CUDA, cudaGetErrorString(e));
+    return KLP_OK;
+}
+
+int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d_a_incl, void* d_out, void* cuda_stream) {
+    if (!t || !d_a_incl || !d_out || B < 0) return fail(KLP_ERR_ARG, "bad argument");
+    if (B == 0) return KLP_OK;
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    const int grid = (int)std::min<long long>(B, (long long)t->sm_count * 8);
+    if (precision == KLP_F32) {
+        BlendArgs<float> a{table_dev(t), d_a_incl, B, (float*)d_out};
+        k_blend<float><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    } else if (precision == KLP_F64) {
+        BlendArgs<double> a{table_dev(t), d_a_incl, B, (double*)d_out};
+        k_blend<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    } else {
+        return fail(KLP_ERR_ARG, "unknown precision");
+    }
+    KLP_CUDA(cudaGetLastError());
+    return KLP_OK;
+}
+
+int klp_set_timing(klp_table* t, int enable) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    t->timing = enable != 0;
+    return KLP_OK;
+}
+
+int klp_get_timing(klp_table* t, double* ms4, long* launches4) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    DeviceGuard dg(t->device);
+    for (int k = 0; k < 4; ++k) { t->ms[k] = 0; t->launches[k] = 0; }
+    for (auto& u : t->ev_used) {
+        auto& p = t->ev_pool[u.second];
+        KLP_CUDA(cudaEventSynchronize(p.second));
+        float ms = 0;
+        KLP_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        t->ms[u.first] += ms;
+        t->launches[u.first] += 1;
+    }
+    for (int k = 0; k < 4; ++k) {
+        if (ms4) ms4[k] = t->ms[k];
+        if (launches4) launches4[k] = t->launches[k];
+    }
+    return KLP_OK;
+}
+
+int klp_set_option(klp_table* t, const char* key, long value) {
+    if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
+    std::string k(key);
+    if (k == "quad_threads") {
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
+        t->quad_threads = (int)value;
+    } else if (k == "splits") {
+        if (value < 0 || value > kNGroups) return fail(KLP_ERR_ARG, "splits");
+        t->splits = (int)value;
+    } else if (k == "chunk") {
+        if (value < 1 || value > 65535) return fail(KLP_ERR_ARG, "chunk");
+        t->chunk = value;
+    } else {
+        return fail(KLP_ERR_ARG, "unknown option");
+    }
+    return KLP_OK;
+}
+
+int klp_fma_peak_gflops(klp_table* t, int precision, double* gflops) {
+    if (!t || !gflops) return fail(KLP_ERR_ARG, "null argument");
+    DeviceGuard dg(t->device);
+    Buf sink;
+    int rc;
+    if ((rc = sink.ensure(64))) return rc;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int grid = t->sm_count * 8, iters = 1 << 15;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        if (precision == KLP_F32) k_fma_peak<float><<<grid, 256>>>((float*)sink.p, iters);
+        else k_fma_peak<double><<<grid, 256>>>((double*)sink.p, iters);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double fl = (double)grid * 256.0 * iters * 8.0 * 2.0;
+        if (ms > 0) best = std::max(best, fl / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    sink.release();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(KLP_ERR_CUDA, cudaGetErrorString(e));
+    *gflops = best;
+    return KLP_OK;
+}
+
+// ---- XSPEC model surface (xspec-wrapper.zig:425-530) ----------------------------------------
+namespace {
+const char* kMsgPrefix = "kerrlineprofile: ";              // xspec-wrapper.zig:12
+const char* kDataDirEnv = "KLINE_PROF_DATA_DIR";           // xspec-wrapper.zig:10
+const char* kModelFile = "kerr-transfer-functions.klpt";   // flat-container twin of xspec-wrapper.zig:11
+std::mutex g_legacy_mu;
+klp_table* g_default_table = nullptr;  // installed by the caller
+klp_table* g_owned_table = nullptr;    // lazily loaded singleton (xspec-wrapper.zig:61)
+int g_legacy_precision = KLP_F32;
+bool g_have_lims = false;              // Q2 ratchet state
+double g_lims[2] = {0, 0};
+
+int legacy_table(klp_table** out) {
+    if (g_default_table) { *out = g_default_table; return KLP_OK; }
+    if (!g_owned_table) {
+        const char* root = std::getenv(kDataDirEnv);
+        std::string path = std::string(root ? root : ".") + "/" + kModelFile;  // getModelPath, :30-48
+        int dev = 0;
+        if (const char* d = std::getenv("KLINE_PROF_DEVICE")) dev = std::atoi(d);
+        int rc = klp_table_load(path.c_str(), dev, &g_owned_table);
+        if (rc) return rc;
+    }
+    *out = g_owned_table;
+    return KLP_OK;
+}
+
+void legacy_call(int model, const double* energy, int n_flux, const double* params, double* flux) {
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    klp_table* t = nullptr;
+    int rc = legacy_table(&t);
+    if (rc == KLP_OK) {
+        EvalExtra ex;
+        ex.use_limits = g_have_lims;
+        ex.lim_lo = g_lims[0];
+        ex.lim_hi = g_lims[1];
+        ex.want_lims = true;
+        std::vector<double> spec;
+        const double* sp = nullptr;
+        if (model >= 2) { spec.assign(flux, flux + n_flux); sp = spec.data(); }  // flux_copy, :200-201
+        std::vector<double> outv((size_t)std::max(n_flux, 1));
+        double lims[2];
+        rc = eval_host(t, model, g_legacy_precision, 1, params, energy, n_flux, sp, 0, outv.data(), ex, lims);
+        if (rc == KLP_OK) {
+            std::memcpy(flux, outv.data(), sizeof(double) * (size_t)n_flux);
+            g_have_lims = true;
+            g_lims[0] = lims[0];
+            g_lims[1] = lims[1];
+            return;
+        }
+    }
+    // xspec-wrapper.zig:361-372
+    if (rc == KLP_ERR_IO)
+        std::fprintf(stderr, "error: %sFailed to find table model. Set the %s environment variable to where %s is located\n",
+                     kMsgPrefix, kDataDirEnv, kModelFile);
+    else
+        std::fprintf(stderr, "error: %s%s\n", kMsgPrefix, g_err.c_str());
+    std::fprintf(stderr, "error: %sMODEL OUTPUT SET TO ZERO\n", kMsgPrefix);
+    if (flux && n_flux > 0) std::memset(flux, 0, sizeof(double) * (size_t)n_flux);
+}
+}  // namespace
+
+void klp_set_default_table(klp_table* t) {
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    g_default_table = t;
+}
+void klp_set_legacy_precision(int precision) {
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    if (precision == KLP_F32 || precision == KLP_F64) g_legacy_precision = precision;
+    g_have_lims = false;
+}
+void klp_legacy_reset(void) {
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    g_have_lims = false;
+}
+
+void kline(const double* energy, int n_flux, const double* params, int, double* flux, double*, const char*) {
+    legacy_call(KLP_KLINE, energy, n_flux, params, flux);
+}
+void kline5(const double* energy, int n_flux, const double* params, int, double* flux, double*, const char*) {
+    legacy_call(KLP_KLINE5, energy, n_flux, params, flux);
+}
+void kconv(const double* energy, int n_flux, const double* params, int, double* flux, double*, const char*) {
+    legacy_call(KLP_KCONV, energy, n_flux, params, flux);
+}
+void kconv5(const double* energy, int n_flux, const double* params, int, double* flux, double*, const char*) {
+    legacy_call(KLP_KCONV5, energy, n_flux, params, flux);
+}
+void kconv10(const double* energy, int n_flux, const double* params, int, double* flux, double*, const char*) {
+    legacy_call(KLP_KCONV10, energy, n_flux, params, flux);
+}
+
+}  // extern "C"

@@ -56,7 +56,8 @@ int klp_model_nparams(int model);
 /* ---- transfer-function table (replaces reference io.readFitsFile, io.zig:53-87, and
  *      LineProfileTable.init, line-profile.zig:233-273) ------------------------------------ */
 
-/* Build a table from host arrays and upload it to `device`.
+/* Build a table from host arrays and upload it to `device` (device = -1: host-only table for the
+ * index helpers below; evaluation entry points then return KLP_ERR_CUDA).
  *   spins[n_a], mus[n_mu] ascending (HDU2 / HDU3 of the reference FITS file; mus are cos(incl));
  *   radii/gmin/gmax [n_a*n_mu][n_r] (radii descending within a frame);
  *   upper/lower     [n_a*n_mu][n_r][n_g];

@@ -51,7 +51,8 @@ struct DeviceGuard {
     int prev = -1;
     bool ok = true;
     explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (dev < 0) { ok = false; return; }  // host-only table
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; return; }
         if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
@@ -333,7 +334,7 @@ int eval_device(klp_table* t, int model, int precision, long long B, const doubl
     if (!d_params || !d_energy || (!d_out && !stop_after_profile)) return fail(KLP_ERR_ARG, "null buffer");
     if (model >= 2 && !d_spec && !stop_after_profile) return fail(KLP_ERR_ARG, "convolution models need an input spectrum");
     DeviceGuard dg(t->device);
-    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     if (t->timing) { t->ev_next = 0; t->ev_used.clear(); }
     if (precision == KLP_F32)
         return eval_device_t<float>(t, model, B, d_params, d_energy, n_flux, d_spec, per_set, d_out, st, ex, stop_after_profile);
@@ -369,7 +370,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         if (!(energy[i + 1] > energy[i])) return fail(KLP_ERR_ARG, "energy edges must be strictly ascending");
     std::lock_guard<std::mutex> lk(t->mu_);
     DeviceGuard dg(t->device);
-    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     int rc;
     if ((rc = ensure_streams(t))) return rc;
     if ((rc = t->d_energy.ensure(sizeof(double) * (size_t)(n_flux + 1)))) return rc;
@@ -461,6 +462,20 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     *out = nullptr;
     if (!spins || !mus || !radii || !gmin || !gmax || !upper || !lower) return fail(KLP_ERR_ARG, "null table array");
     if (n_a < 1 || n_mu < 1 || n_r < 3 || n_g < 2 || n_g > kMaxNG) return fail(KLP_ERR_ARG, "bad table dimensions");
+    for (int i = 1; i < n_a; ++i) if (!(spins[i] > spins[i - 1])) return fail(KLP_ERR_ARG, "spins must be strictly ascending");
+    for (int i = 1; i < n_mu; ++i) if (!(mus[i] > mus[i - 1])) return fail(KLP_ERR_ARG, "mus must be strictly ascending");
+    const size_t frame_len = (size_t)n_r * (2 * n_g + 3);
+    if (device == -1) {
+        // host-only table: index logic works, every evaluation entry point refuses (no CPU path)
+        klp_table* t = new klp_table;
+        t->device = -1;
+        t->n_a = n_a; t->n_mu = n_mu; t->n_r = n_r; t->n_g = n_g;
+        t->spins.assign(spins, spins + n_a);
+        t->mus.assign(mus, mus + n_mu);
+        t->frame_stride = (frame_len + 3) & ~(size_t)3;
+        *out = t;
+        return KLP_OK;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(KLP_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -472,7 +487,6 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     t->n_a = n_a; t->n_mu = n_mu; t->n_r = n_r; t->n_g = n_g;
     t->spins.assign(spins, spins + n_a);
     t->mus.assign(mus, mus + n_mu);
-    const size_t frame_len = (size_t)n_r * (2 * n_g + 3);
     t->frame_stride = (frame_len + 3) & ~(size_t)3;
     const size_t F = (size_t)n_a * n_mu;
     cudaDeviceProp prop;
@@ -543,7 +557,7 @@ int klp_table_load(const char* path, int device, klp_table** out) {
 
 void klp_table_destroy(klp_table* t) {
     if (!t) return;
-    {
+    if (t->device >= 0) {
         DeviceGuard dg(t->device);
         cudaDeviceSynchronize();
         if (t->d_frames) cudaFree(t->d_frames);
@@ -626,7 +640,7 @@ int klp_eval_debug(klp_table* t, int model, int precision, long B, const double*
     if (P < 0 || B < 1 || n_flux < 1 || !params || !energy) return fail(KLP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(t->mu_);
     DeviceGuard dg(t->device);
-    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     if (B > t->chunk) return fail(KLP_ERR_ARG, "klp_eval_debug: B must fit one chunk");
     int rc;
     if ((rc = ensure_streams(t))) return rc;
@@ -667,7 +681,7 @@ int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d
     if (!t || !d_a_incl || !d_out || B < 0) return fail(KLP_ERR_ARG, "bad argument");
     if (B == 0) return KLP_OK;
     DeviceGuard dg(t->device);
-    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's CUDA device");
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     const int grid = (int)std::min<long long>(B, (long long)t->sm_count * 8);
     if (precision == KLP_F32) {
         BlendArgs<float> a{table_dev(t), d_a_incl, B, (float*)d_out};

@@ -1,0 +1,93 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/*.h declares, the host-side
+index logic matches the reference's known answers, and evaluation refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lineprofiles_b200 as klp
+from lineprofiles_b200 import synthetic as syn
+from lineprofiles_b200 import tableio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "klineprofiles_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text)
+    return sorted(set(n for n in names if n.startswith("klp_") or n in klp.MODELS))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(klp.library_path())
+    syms = _declared_symbols()
+    assert {"kline", "kline5", "kconv", "kconv5", "kconv10", "klp_eval_batch", "klp_eval_batch_device",
+            "klp_table_create", "klp_table_load"} <= set(syms)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+
+
+def test_parameter_counts_match_lmodel_dat():
+    lib = klp.load_library()
+    # reference xspec/lmodel.dat:1,9,23,30,43
+    assert [lib.klp_model_nparams(m) for m in range(5)] == [6, 12, 5, 11, 16]
+    assert lib.klp_model_nparams(9) == -1
+
+
+def test_host_index_logic_known_answers(table_arrays):
+    """main.zig:19-30 through the product library's host-side mirror (host-only table, no GPU needed)."""
+    t = klp.Table.from_arrays(table_arrays, device=-1)
+    assert (t.n_a, t.n_mu, t.n_r, t.n_g) == (30, 20, 150, 30)
+    assert t.table_index(27, 12) == 552 and t.table_index(0, 12) == 12
+    assert t.find_tables([27, 12]) == [532, 552, 531, 551]
+    assert t.find_tables([0, 1]) == [1, 1, 0, 0]
+    assert t.find_parameter_indices(0.92, 0.4) == [24, 8]
+    assert t.find_parameter_indices(5.0, 5.0) == [0, 0]          # Q5
+    assert t.parameter_weight(0, 0.1, 0) is None
+    w = t.parameter_weight(1, 0.4, 8)
+    m = table_arrays["mus"]
+    assert abs(w - (np.float32(0.4) - m[7]) / (m[8] - m[7])) < 1e-6
+    t.close()
+
+
+def test_evaluation_refuses_without_device(table_arrays):
+    t = klp.Table.from_arrays(table_arrays, device=-1)
+    with pytest.raises(klp.KlpError, match="no CPU path"):
+        t.eval_batch("kline", syn.CONFIG1_PARAMS, syn.energy_grid_linear(10))
+    t.close()
+
+
+def test_bad_arguments_are_rejected(table_arrays):
+    bad = dict(table_arrays)
+    bad["spins"] = table_arrays["spins"][::-1].copy()
+    with pytest.raises(klp.KlpError, match="ascending"):
+        klp.Table.from_arrays(bad, device=-1)
+    with pytest.raises(klp.KlpError):
+        klp.Table.load("/nonexistent/table.klpt", device=-1)
+
+
+def test_table_file_roundtrip(tmp_path, table_arrays):
+    small = syn.make_table(3, 4, 9, 30)
+    p = str(tmp_path / "t.klpt")
+    tableio.save_table(p, small)
+    back = tableio.load_table(p)
+    for k in ("spins", "mus", "radii", "gmin", "gmax", "upper", "lower"):
+        assert np.array_equal(back[k], small[k])
+    (tmp_path / "bad.klpt").write_bytes(b"NOTATABLE")
+    with pytest.raises(klp.KlpError, match="KLPT0001"):
+        klp.Table.load(str(tmp_path / "bad.klpt"), device=-1)
+
+
+def test_xspec_symbols_zero_fill_on_error(tmp_path, capfd, monkeypatch):
+    """xspec-wrapper.zig:361-372: failures are logged with the kerrlineprofile prefix and the output zeroed."""
+    monkeypatch.setenv("KLINE_PROF_DATA_DIR", str(tmp_path))   # no table there
+    klp.set_default_table(None)
+    E = syn.energy_grid_linear(20)
+    flux = np.full(20, 7.0)
+    klp.kline(E, syn.CONFIG1_PARAMS[0], flux)
+    err = capfd.readouterr().err
+    assert np.all(flux == 0)
+    assert "kerrlineprofile: " in err and "MODEL OUTPUT SET TO ZERO" in err and "KLINE_PROF_DATA_DIR" in err

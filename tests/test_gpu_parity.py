@@ -1,0 +1,283 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full batch
+sizes -- through size-independent properties.
+
+Tolerance (BASELINE.json north_star / SURVEY.md §8d): every bin |x - y| <= 1e-6 |y| + 1e-12 max|y|.
+In f32 ("reference-faithful") mode the CUDA path issues the oracle's operations in the oracle's order,
+so additionally the fine-grid flux must be bit-identical in (almost) every bin; the only permitted
+source of differences is the last f64 ulp of cos/pow/log10 (CUDA vs glibc).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import lineprofiles_b200 as klp
+from lineprofiles_b200 import synthetic as syn
+from lineprofiles_b200 import tableio
+from oracle import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL, AFLOOR = 1e-6, 1e-12
+MODELS = ("kline", "kline5", "kconv", "kconv5", "kconv10")
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz")
+
+
+def assert_parity(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w), f"{what}: NaN pattern differs"
+    g, w = np.where(nan_g, 0, got), np.where(nan_w, 0, want)
+    scale = np.max(np.abs(w), axis=-1, keepdims=True)
+    bad = np.abs(g - w) > RTOL * np.abs(w) + AFLOOR * scale
+    assert not bad.any(), f"{what}: {bad.sum()} bins out of tolerance, worst rel {np.max(np.abs(g - w) / (np.abs(w) + AFLOOR * scale)):.3e}"
+
+
+def grids(model):
+    if model.startswith("kconv"):
+        E = syn.energy_grid_log(512)
+        return E, syn.powerlaw_continuum(E)
+    return syn.energy_grid_linear(1000), None
+
+
+def test_config1_single_kline(gpu_table, oracle_table):
+    """BASELINE config 1: kline a=0.998 incl=30 eline=6.4 rmin=ISCO rout=400 alpha=3 on the 1000-bin grid."""
+    E = syn.energy_grid_linear(1000)
+    for prec in ("f32", "f64"):
+        got = gpu_table.eval_batch("kline", syn.CONFIG1_PARAMS, E, precision=prec)
+        want = oracle_table.eval_batch("kline", syn.CONFIG1_PARAMS, E, precision=prec, faithful_cost=True)["out"]
+        assert_parity(got, want, f"config1 {prec}")
+        assert abs(got.sum() - 1) < 1e-12
+    got32 = gpu_table.eval_batch("kline", syn.CONFIG1_PARAMS, E, precision="f32")
+    want32 = oracle_table.eval_batch("kline", syn.CONFIG1_PARAMS, E, precision="f32")["out"]
+    assert np.array_equal(got32, want32), "f32 mode is expected to be bit-identical on config 1"
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_random_sets_all_models(gpu_table, oracle_table, model, prec):
+    E, spec = grids(model)
+    p = syn.random_params(model, 48, seed=2024)
+    got = gpu_table.eval_batch(model, p, E, spectrum=spec, precision=prec)
+    ref = oracle_table.eval_batch(model, p, E, spectrum=spec, precision=prec, threads=os.cpu_count() or 1, want_fine=True,
+                                  want_profile=spec is not None)
+    assert_parity(got, ref["out"], f"{model} {prec}")
+    fine, prof = gpu_table.eval_debug(model, p, E, precision=prec)
+    assert_parity(fine, ref["fine"], f"{model} {prec} fine grid")
+    if prof is not None:
+        assert_parity(prof, ref["profile"], f"{model} {prec} profile")
+    if prec == "f32":
+        frac = np.mean(fine == ref["fine"])
+        assert frac > 0.999, f"f32 fine flux bit-identical in only {frac:.5f} of the bins"
+
+
+def test_golden_vectors(gpu_table):
+    g = np.load(GOLD)
+    for model in MODELS:
+        conv = model.startswith("kconv")
+        for prec in ("f32", "f64"):
+            got = gpu_table.eval_batch(model, g[f"params_{model}"], g["energy_conv"] if conv else g["energy_line"],
+                                       spectrum=g["spectrum"] if conv else None, precision=prec)
+            assert_parity(got, g[f"out_{model}_{prec}"], f"golden {model} {prec}")
+
+
+def test_reference_smoke_vectors(gpu_table, oracle_table):
+    """The parameter vectors of xspec-wrapper.zig:553-585 (including the stale kline order that puts
+    rmin=3 > rmax=1, and rmin = rmax = 0 which makes every weight NaN -> all-NaN output, Q10)."""
+    dom, _ = orc.range_iterator(0.1, 10.0, 100, "f64")
+    vecs = np.array([[0.998, 60, 6.4, 3.0, 1.0, 400.0], [0.998, 0.1, 6.4, 3.0, 1.0, 400.0], [0.998, 89.0, 6.4, 3.0, 1.0, 400.0],
+                     [0.998, 60.0, 6.4, 0.0, 1.0, 400.0], [0.998, 60.0, 6.4, 0.0, 0.0, 400.0]])
+    for prec in ("f32", "f64"):
+        got = gpu_table.eval_batch("kline", vecs, dom, precision=prec)
+        want = oracle_table.eval_batch("kline", vecs, dom, precision=prec)["out"]
+        assert_parity(got, want, f"smoke kline {prec}")
+        flux = np.ones(99)
+        for model, v in (("kconv5", [0.998, 60.0, 1.0, 400.0, 100.0, 3.0, 3.0, 3.0, 3.0, 3.0, 3.0]),
+                         ("kconv10", [0.998, 60.0, 1.0, 400.0, 50.0, 3.0] + [3.0] * 10)):
+            got = gpu_table.eval_batch(model, np.array([v]), dom, spectrum=flux, precision=prec)
+            want = oracle_table.eval_batch(model, np.array([v]), dom, spectrum=flux, precision=prec)["out"]
+            assert_parity(got, want, f"smoke {model} {prec}")
+
+
+def test_edge_parameters(gpu_table, oracle_table):
+    """Out-of-table spin / inclination (Q5 snap), grazing and face-on inclinations, rmin > rmax, zero knots."""
+    E = syn.energy_grid_linear(400)
+    base = syn.random_params("kline5", 10, seed=31)
+    base[0, 0] = 1.7          # above the spin grid -> first frame
+    base[1, 0] = -0.9         # below the spin grid
+    base[2, 1] = 0.0          # cos = 1 above the mu grid
+    base[3, 1] = 90.0         # cos ~ 0 below the mu grid
+    base[4, 3:5] = (30.0, 10.0)   # rmin > rmax
+    base[5, 7:] = 0.0         # all emissivity knots zero (the reference's "with zero emissivities" case)
+    base[6, 5] = 1.0          # rcut = 1 -> log10(rcut) = 0, every knot radius = 1
+    base[7, 3:5] = (1.0, 1000.0)
+    base[8, 2] = 0.5          # eline far below the grid centre
+    base[9, 6] = 10.0         # steep outer index
+    for prec in ("f32", "f64"):
+        got = gpu_table.eval_batch("kline5", base, E, precision=prec)
+        want = oracle_table.eval_batch("kline5", base, E, precision=prec)["out"]
+        assert_parity(got, want, f"edge params {prec}")
+
+
+@pytest.mark.parametrize("n_bins", [1, 2, 7, 100, 2500])
+def test_ragged_energy_grids(gpu_table, oracle_table, n_bins):
+    rng = np.random.default_rng(n_bins)
+    E = np.sort(rng.uniform(0.3, 9.0, n_bins + 1))
+    E += np.arange(n_bins + 1) * 1e-9   # strictly ascending
+    p = syn.random_params("kline", 3, seed=n_bins)
+    got = gpu_table.eval_batch("kline", p, E, precision="f32")
+    want = oracle_table.eval_batch("kline", p, E, precision="f32")["out"]
+    assert_parity(got, want, f"ragged kline n={n_bins}")
+    spec = rng.uniform(0, 1, n_bins)
+    pc = syn.random_params("kconv", 3, seed=n_bins)
+    got = gpu_table.eval_batch("kconv", pc, E, spectrum=spec, precision="f32")
+    want = oracle_table.eval_batch("kconv", pc, E, spectrum=spec, precision="f32")["out"]
+    assert_parity(got, want, f"ragged kconv n={n_bins}")
+
+
+def test_config3_grid_kconv_4096(gpu_table, oracle_table):
+    """BASELINE config 3 grid (4096-bin log grid, shared power-law continuum), a few sets against the oracle."""
+    E = syn.energy_grid_log(4096)
+    spec = syn.powerlaw_continuum(E)
+    p = syn.random_params("kconv", 4, seed=20261)
+    got = gpu_table.eval_batch("kconv", p, E, spectrum=spec, precision="f32")
+    want = oracle_table.eval_batch("kconv", p, E, spectrum=spec, precision="f32", threads=4)["out"]
+    assert_parity(got, want, "kconv 4096")
+
+
+def test_per_set_spectrum_equals_shared(gpu_table):
+    E = syn.energy_grid_log(300)
+    spec = syn.powerlaw_continuum(E)
+    p = syn.random_params("kconv10", 5, seed=3)
+    a = gpu_table.eval_batch("kconv10", p, E, spectrum=spec, precision="f32")
+    b = gpu_table.eval_batch("kconv10", p, E, spectrum=np.tile(spec, (5, 1)), precision="f32")
+    assert np.array_equal(a, b)
+
+
+def test_invariance_to_batching_knobs(gpu_table):
+    """Sets are independent: the result of a set must not depend on batch order, chunking, CTA splitting or CTA size."""
+    E = syn.energy_grid_linear(1000)
+    p = syn.random_params("kline5", 700, seed=55)
+    base = gpu_table.eval_batch("kline5", p, E, precision="f32")
+    perm = np.random.default_rng(0).permutation(700)
+    assert np.array_equal(gpu_table.eval_batch("kline5", p[perm], E, precision="f32"), base[perm])
+    try:
+        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 128), ("quad_threads", 512)):
+            gpu_table.set_option(key, val)
+            assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
+            gpu_table.set_option(key, {"chunk": 16384, "splits": 0, "quad_threads": 0}[key])
+    finally:
+        for key, val in (("chunk", 16384), ("splits", 0), ("quad_threads", 0)):
+            gpu_table.set_option(key, val)
+
+
+def test_device_entry_equals_host_entry(gpu_table):
+    import torch
+    E = syn.energy_grid_linear(1000)
+    p = syn.random_params("kline5", 300, seed=8)
+    host = gpu_table.eval_batch("kline5", p, E, precision="f64")
+    dp, dE = torch.from_numpy(p).cuda(), torch.from_numpy(E).cuda()
+    out = torch.empty((300, 1000), dtype=torch.float64, device="cuda")
+    gpu_table.eval_batch_device("kline5", dp, dE, 1000, out, 300, precision="f64", stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)
+
+
+def test_blend_kernel_matches_oracle(gpu_table, oracle_table, table_arrays):
+    import torch
+    rng = np.random.default_rng(12)
+    ai = np.stack([rng.uniform(-0.2, 1.1, 64), rng.uniform(0, 90, 64)], axis=1)
+    n_r, n_g = table_arrays["n_r"], table_arrays["n_g"]
+    for prec, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        out = torch.empty((64, n_r * (2 * n_g + 3)), dtype=dt, device="cuda")
+        gpu_table.blend_frames_device(torch.from_numpy(ai).cuda(), out, 64, precision=prec)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.float64)
+        for s in range(64):
+            fr = oracle_table.blend_frame(ai[s, 0], ai[s, 1], prec)
+            want = np.concatenate([fr["radii"], fr["gmin"], fr["gmax"], fr["upper"].ravel(), fr["lower"].ravel()])
+            assert np.mean(got[s] == want) > 0.999 and np.allclose(got[s], want, rtol=1e-6), (prec, s)
+
+
+def test_big_table_rows_in_global_scratch(oracle_table):
+    """A frame too large for shared memory (n_r * (2 n_g + 3) * 4 B > 227 KB) takes the per-CTA scratch path."""
+    tab = syn.make_table(4, 3, 700, 48)
+    gt = klp.Table.from_arrays(tab, 0)
+    ot = orc.OracleTable(tab)
+    E = syn.energy_grid_linear(200)
+    p = syn.random_params("kline", 6, seed=1)
+    assert_parity(gt.eval_batch("kline", p, E, precision="f32"), ot.eval_batch("kline", p, E, precision="f32")["out"], "scratch f32")
+    assert_parity(gt.eval_batch("kline", p, E, precision="f64"), ot.eval_batch("kline", p, E, precision="f64")["out"], "scratch f64")
+    gt.close()
+
+
+def test_table_file_load_on_device(tmp_path, gpu_table, table_arrays):
+    p = str(tmp_path / "kerr-transfer-functions.klpt")
+    tableio.save_table(p, table_arrays)
+    t2 = klp.Table.load(p, 0)
+    E = syn.energy_grid_linear(100)
+    a = t2.eval_batch("kline", syn.CONFIG1_PARAMS, E)
+    assert np.array_equal(a, gpu_table.eval_batch("kline", syn.CONFIG1_PARAMS, E))
+    t2.close()
+
+
+def test_xspec_symbols_and_ratchet(gpu_table, oracle_table):
+    """The five exported XSPEC symbols, including the reference's radial-limit ratchet (Q2) across calls."""
+    klp.set_default_table(gpu_table)
+    klp.set_legacy_precision("f32")
+    klp.legacy_reset()
+    try:
+        E = syn.energy_grid_linear(100)
+        calls = np.array([[0.5, 40, 6.4, 5.0, 20.0, 3.0], [0.5, 40, 6.4, 1.0, 400.0, 3.0], [0.9, 70, 6.4, 8.0, 15.0, 2.0]])
+        lo, hi = orc.base_limits("f32")
+        want = oracle_table.eval_batch("kline", calls, E, precision="f32", ratchet=True, lims=[lo, hi])["out"]
+        for k in range(3):
+            got = klp.kline(E, calls[k])
+            assert_parity(got, want[k], f"ratchet call {k}")
+        klp.legacy_reset()
+        fresh = oracle_table.eval_batch("kline", calls[1:2], E, precision="f32")["out"][0]
+        assert_parity(klp.kline(E, calls[1]), fresh, "after reset")
+        # the other four symbols, fresh process each
+        spec = syn.powerlaw_continuum(E)
+        for name, fn in (("kline5", klp.kline5), ("kconv", klp.kconv), ("kconv5", klp.kconv5), ("kconv10", klp.kconv10)):
+            klp.legacy_reset()
+            p = syn.random_params(name, 1, seed=99)[0]
+            conv = name.startswith("kconv")
+            flux = spec.copy() if conv else None
+            got = fn(E, p, flux)
+            want = oracle_table.eval_batch(name, p[None], E, spectrum=spec if conv else None, precision="f32")["out"][0]
+            assert_parity(got, want, name)
+    finally:
+        klp.set_default_table(None)
+        klp.legacy_reset()
+
+
+def test_full_batch_properties_config2(gpu_table, oracle_table):
+    """BASELINE config 2 at full size (kline5, B = 1e5): properties that need no oracle at that size, plus an
+    oracle comparison of a random subsample."""
+    B = 100000
+    E = syn.energy_grid_linear(1000)
+    p = syn.random_params("kline5", B)
+    out = gpu_table.eval_batch("kline5", p, E, precision="f32")
+    assert out.shape == (B, 1000) and np.isfinite(out).all() and (out >= 0).all()
+    np.testing.assert_allclose(out.sum(axis=1), 1.0, rtol=1e-12)     # Q10: every spectrum sums to one
+    idx = np.random.default_rng(1).choice(B, 64, replace=False)
+    want = oracle_table.eval_batch("kline5", p[idx], E, precision="f32", threads=os.cpu_count() or 1)["out"]
+    assert_parity(out[idx], want, "config 2 subsample")
+    # idempotence: a second evaluation of a slice reproduces the batch result bit for bit
+    assert np.array_equal(gpu_table.eval_batch("kline5", p[5000:5600], E, precision="f32"), out[5000:5600])
+
+
+def test_conv_linearity_config3_grid(gpu_table):
+    """The convolution is linear in the input spectrum: conv(a*s1 + s2) == a*conv(s1) + conv(s2) to rounding."""
+    E = syn.energy_grid_log(4096)
+    s1 = syn.powerlaw_continuum(E)
+    s2 = np.zeros(4096)
+    s2[[1000, 2500, 3000]] = 1e-2
+    p = syn.random_params("kconv", 256, seed=20261)
+    c1 = gpu_table.eval_batch("kconv", p, E, spectrum=s1, precision="f32")
+    c2 = gpu_table.eval_batch("kconv", p, E, spectrum=s2, precision="f32")
+    c3 = gpu_table.eval_batch("kconv", p, E, spectrum=3.0 * s1 + s2, precision="f32")
+    np.testing.assert_allclose(c3, 3.0 * c1 + c2, rtol=1e-9, atol=1e-18)

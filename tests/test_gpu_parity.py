@@ -198,7 +198,11 @@ def test_blend_kernel_matches_oracle(gpu_table, oracle_table, table_arrays):
         for s in range(64):
             fr = oracle_table.blend_frame(ai[s, 0], ai[s, 1], prec)
             want = np.concatenate([fr["radii"], fr["gmin"], fr["gmax"], fr["upper"].ravel(), fr["lower"].ravel()])
-            assert np.mean(got[s] == want) > 0.999 and np.allclose(got[s], want, rtol=1e-6), (prec, s)
+            # f32: same operations in the same order -> bit-identical; f64: cos() differs in its last ulp
+            # between CUDA and glibc, which perturbs the mu weight at the 1e-16 level
+            if prec == "f32":
+                assert np.mean(got[s] == want) > 0.999, (prec, s)
+            assert np.allclose(got[s], want, rtol=1e-6 if prec == "f32" else 1e-12), (prec, s)
 
 
 def test_big_table_rows_in_global_scratch(oracle_table):

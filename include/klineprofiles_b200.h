@@ -125,8 +125,16 @@ int klp_set_timing(klp_table* t, int enable);
 int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 
 /* Tuning knobs (testing / benchmarking): "quad_threads" (128..1024), "splits" (CTAs per set,
- * 0 = auto), "chunk" (sets per internal chunk). */
+ * 0 = auto), "chunk" (sets per internal chunk), "fast" (1 = allow the branch-free exact-arithmetic
+ * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
+ * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);
+
+/* Self-test of the branch-free exact-arithmetic sequences (klp_kernels.cuh: div_by, div_gen, sqrt_gen)
+ * against the IEEE intrinsics on n_total random + adversarial operands drawn from the ranges they are
+ * licensed for.  mismatches4: f32 div_by, f64 div_by, f32 div_gen, f32 sqrt_gen -- all must be 0. */
+int klp_arith_selftest(klp_table* t, unsigned long long seed, unsigned long long n_total,
+                       unsigned long long* mismatches4);
 
 /* Peak-rate microbenchmark on the table's device: dependent-chain-free FMA throughput in
  * GFLOP/s for precision f32 / f64 (denominator of the compute roofline). */

@@ -64,6 +64,7 @@ def load_library():
     L.klp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_long)]
     L.klp_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.klp_fma_peak_gflops.argtypes = [vp, C.c_int, dp]
+    L.klp_arith_selftest.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     sig = [dp, C.c_int, dp, C.c_int, dp, dp, C.c_char_p]
     for name in MODELS:
         fn = getattr(L, name)
@@ -231,6 +232,11 @@ class Table:
 
     def set_option(self, key: str, value: int) -> None:
         _check(load_library().klp_set_option(self._h, key.encode(), int(value)), "klp_set_option")
+
+    def arith_selftest(self, n_total: int, seed: int = 1):
+        m = (C.c_ulonglong * 4)()
+        _check(load_library().klp_arith_selftest(self._h, seed, int(n_total), m), "klp_arith_selftest")
+        return dict(zip(("f32_div_by", "f64_div_by", "f32_div_gen", "f32_sqrt_gen"), (int(v) for v in m)))
 
     def fma_peak_gflops(self, precision: str = "f32") -> float:
         g = C.c_double()

@@ -117,6 +117,8 @@ struct klp_table {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // options
     int quad_threads = 0;  // 0 = auto
+    bool fast_ok = false;  // table values within the binades that license the FAST arithmetic (klp_kernels.cuh)
+    bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     long chunk = 16384;
     // timing
@@ -159,16 +161,10 @@ template <class T> CallConsts<T>* cc_ptr(klp_table* t);
 template <> CallConsts<float>* cc_ptr<float>(klp_table* t) { return (CallConsts<float>*)t->cc32.p; }
 template <> CallConsts<double>* cc_ptr<double>(klp_table* t) { return (CallConsts<double>*)t->cc64.p; }
 
-template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, int& grid_out, cudaStream_t st, bool dry) {
-    const int NW = NT / 32;
-    size_t fixed = QuadSmem<T>::fixed_bytes(t->n_g, NW);
-    size_t fb = QuadSmem<T>::frame_bytes(t->n_r, t->n_g);
-    bool in_smem = fixed + fb <= (size_t)t->max_smem_optin;
-    size_t smem = fixed + (in_smem ? fb : 0);
-    if (smem > (size_t)t->max_smem_optin) return fail(KLP_ERR_ARG, "table rows too wide for shared memory");
-    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, QuadArgs<T>& q, size_t smem, size_t fb, cudaStream_t st) {
+    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT>, NT, smem));
+    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM>, NT, smem));
     if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
@@ -179,29 +175,34 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, int&
     splits = std::max(1, std::min(splits, kNGroups));
     q.splits = splits;
     const long long items = q.B * splits;
-    int grid = (int)std::min<long long>(items, resident);
-    grid_out = grid;
-    q.frame_in_smem = in_smem ? 1 : 0;
-    if (!in_smem) {
+    const int grid = (int)std::min<long long>(items, resident);
+    if (!FRAME_SMEM) {
         int rc = t->scratch.ensure((size_t)grid * fb);
         if (rc) return rc;
         q.scratch = (T*)t->scratch.p;
     }
-    if (dry) return KLP_OK;
-    k_quad<T, NT><<<grid, NT, smem, st>>>(q);
+    k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
     KLP_CUDA(cudaGetLastError());
     return KLP_OK;
+}
+
+template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
+    const int NW = NT / 32;
+    const size_t fixed = QuadSmem<T>::fixed_bytes(t->n_g, NW);
+    const size_t fb = QuadSmem<T>::frame_bytes(t->n_r, t->n_g);
+    if (fixed > (size_t)t->max_smem_optin) return fail(KLP_ERR_ARG, "table rows too wide for shared memory");
+    if (fixed + fb <= (size_t)t->max_smem_optin) return launch_quad_impl<T, NT, true>(t, q, fixed + fb, fb, st);
+    return launch_quad_impl<T, NT, false>(t, q, fixed, fb, st);
 }
 
 template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
     int nt = t->quad_threads;
     if (nt <= 0) nt = sizeof(T) == 4 ? 256 : 512;
-    int grid = 0;
     switch (nt) {
-        case 128: return launch_quad_nt<T, 128>(t, q, grid, st, false);
-        case 256: return launch_quad_nt<T, 256>(t, q, grid, st, false);
-        case 512: return launch_quad_nt<T, 512>(t, q, grid, st, false);
-        case 1024: return launch_quad_nt<T, 1024>(t, q, grid, st, false);
+        case 128: return launch_quad_nt<T, 128>(t, q, st);
+        case 256: return launch_quad_nt<T, 256>(t, q, st);
+        case 512: return launch_quad_nt<T, 512>(t, q, st);
+        case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
     return fail(KLP_ERR_ARG, "quad_threads must be 128, 256, 512 or 1024");
 }
@@ -268,7 +269,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.splits = 1;
         q.fine = (T*)t->fine.p;
         q.scratch = nullptr;
-        q.frame_in_smem = 1;
+        q.allow_fast = (t->fast_ok && t->use_fast) ? 1 : 0;
         q.counter = (unsigned long long*)t->counter.p + c;
         q.use_limits = ex.use_limits ? 1 : 0;
         q.lim_lo = (T)ex.lim_lo;
@@ -497,6 +498,16 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     if (cudaMalloc(&t->d_frames, sizeof(float) * F * t->frame_stride) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(frames)");
     if (cudaMalloc(&t->d_spins, sizeof(float) * n_a) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(spins)");
     if (cudaMalloc(&t->d_mus, sizeof(float) * n_mu) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(mus)");
+    {
+        // operand-range precondition of the FAST arithmetic: branches in [2^-20, 2^20], g limits in [2^-10, 2^10]
+        bool ok = true;
+        const size_t nb = F * (size_t)n_r * n_g, nr = F * (size_t)n_r;
+        for (size_t i = 0; i < nb && ok; ++i)
+            ok = upper[i] >= 9.5367431640625e-07f && upper[i] <= 1048576.f && lower[i] >= 9.5367431640625e-07f && lower[i] <= 1048576.f;
+        for (size_t i = 0; i < nr && ok; ++i)
+            ok = gmin[i] >= 0.0009765625f && gmin[i] <= 1024.f && gmax[i] >= 0.0009765625f && gmax[i] <= 1024.f;
+        t->fast_ok = ok;
+    }
     // pack frames: radii | gmin | gmax | upper | lower, padded to the stride; staged in slabs
     const size_t slab_frames = std::max<size_t>(1, (64u << 20) / (sizeof(float) * t->frame_stride));
     std::vector<float> slab(slab_frames * t->frame_stride, 0.f);
@@ -730,12 +741,32 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "splits") {
         if (value < 0 || value > kNGroups) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "fast") {
+        t->use_fast = value != 0;
     } else if (k == "chunk") {
         if (value < 1 || value > 65535) return fail(KLP_ERR_ARG, "chunk");
         t->chunk = value;
     } else {
         return fail(KLP_ERR_ARG, "unknown option");
     }
+    return KLP_OK;
+}
+
+int klp_arith_selftest(klp_table* t, unsigned long long seed, unsigned long long n_total, unsigned long long* mismatches4) {
+    if (!t || !mismatches4) return fail(KLP_ERR_ARG, "null argument");
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table");
+    Buf d;
+    int rc;
+    if ((rc = d.ensure(4 * sizeof(unsigned long long)))) return rc;
+    cudaMemset(d.p, 0, 4 * sizeof(unsigned long long));
+    const int grid = t->sm_count * 8, threads = grid * 256;
+    const unsigned long long per = (n_total + threads - 1) / threads;
+    k_arith_selftest<<<grid, 256>>>(seed, per, (unsigned long long*)d.p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches4, d.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    d.release();
+    if (e != cudaSuccess) return fail(KLP_ERR_CUDA, cudaGetErrorString(e));
     return KLP_OK;
 }
 

@@ -42,6 +42,27 @@ def grids(model):
     return syn.energy_grid_linear(1000), None
 
 
+def test_exact_arithmetic_sequences(gpu_table):
+    """The FAST division / square-root sequences equal the IEEE intrinsics on 2^33 operands per kind."""
+    m = gpu_table.arith_selftest(1 << 33, seed=20261019)
+    assert m == {"f32_div_by": 0, "f64_div_by": 0, "f32_div_gen": 0, "f32_sqrt_gen": 0}, m
+
+
+def test_fast_and_strict_paths_identical(gpu_table):
+    """Option "fast" = 0 forces the plain IEEE-intrinsic path; results must be bit-identical."""
+    E = syn.energy_grid_linear(1000)
+    p = syn.random_params("kline5", 256, seed=91)
+    try:
+        for prec in ("f32", "f64"):
+            gpu_table.set_option("fast", 1)
+            a = gpu_table.eval_batch("kline5", p, E, precision=prec)
+            gpu_table.set_option("fast", 0)
+            b = gpu_table.eval_batch("kline5", p, E, precision=prec)
+            assert np.array_equal(a, b), prec
+    finally:
+        gpu_table.set_option("fast", 1)
+
+
 def test_config1_single_kline(gpu_table, oracle_table):
     """BASELINE config 1: kline a=0.998 incl=30 eline=6.4 rmin=ISCO rout=400 alpha=3 on the 1000-bin grid."""
     E = syn.energy_grid_linear(1000)

@@ -120,7 +120,7 @@ struct klp_table {
     bool fast_ok = false;  // table values within the binades that license the FAST arithmetic (klp_kernels.cuh)
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
-    long chunk = 16384;
+    long chunk = 65535;
     // timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -197,14 +197,15 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cuda
 
 template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
     int nt = t->quad_threads;
-    if (nt <= 0) nt = sizeof(T) == 4 ? 256 : 512;
+    if (nt <= 0) nt = sizeof(T) == 4 ? 512 : 1024;
     switch (nt) {
         case 128: return launch_quad_nt<T, 128>(t, q, st);
         case 256: return launch_quad_nt<T, 256>(t, q, st);
+        case 384: return launch_quad_nt<T, 384>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);
         case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
-    return fail(KLP_ERR_ARG, "quad_threads must be 128, 256, 512 or 1024");
+    return fail(KLP_ERR_ARG, "quad_threads must be 128, 256, 384, 512 or 1024");
 }
 
 TableDev table_dev(const klp_table* t) {
@@ -736,7 +737,7 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
     std::string k(key);
     if (k == "quad_threads") {
-        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
+        if (value != 0 && value != 128 && value != 256 && value != 384 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
         t->quad_threads = (int)value;
     } else if (k == "splits") {
         if (value < 0 || value > kNGroups) return fail(KLP_ERR_ARG, "splits");

@@ -188,9 +188,9 @@ def test_invariance_to_batching_knobs(gpu_table):
         for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 128), ("quad_threads", 512)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
-            gpu_table.set_option(key, {"chunk": 16384, "splits": 0, "quad_threads": 0}[key])
+            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0}[key])
     finally:
-        for key, val in (("chunk", 16384), ("splits", 0), ("quad_threads", 0)):
+        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0)):
             gpu_table.set_option(key, val)
 
 

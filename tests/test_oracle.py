@@ -214,3 +214,22 @@ def test_golden_vectors(oracle_table):
             out = oracle_table.eval_batch(model, g[f"params_{model}"], E, spectrum=spec, precision=prec)["out"]
             want = g[f"out_{model}_{prec}"]
             np.testing.assert_allclose(out, want, rtol=1e-11, atol=1e-300, equal_nan=True)
+
+
+# ---- independent re-derivation ----------------------------------------------------------------------
+def test_numpy_rederivation_agrees_with_oracle(table_arrays, oracle_table):
+    """oracle/numpy_check.py (vectorised, written separately from the reference source) vs the C++ oracle, f64."""
+    from oracle import numpy_check as nc
+    E = syn.energy_grid_linear(1000)
+    p = syn.CONFIG1_PARAMS[0]
+    ref = oracle_table.eval_batch("kline", p[None], E, precision="f64", want_fine=True)
+    fine, g = nc.fine_flux(table_arrays, p[0], p[1], p[2], p[3], p[4], nc.emissivity_fn(p[5]), E[0], E[-1])
+    scale = ref["fine"][0].max()
+    assert np.max(np.abs(fine - ref["fine"][0])) <= 1e-11 * scale
+    np.testing.assert_allclose(nc.rebin(fine, g, E, p[2]), ref["out"][0], rtol=1e-10, atol=1e-16)
+    # a kline5 set (knot emissivity) at a high inclination
+    q = syn.random_params("kline5", 1, seed=77)[0]
+    q[1] = 72.0
+    ref = oracle_table.eval_batch("kline5", q[None], E, precision="f64", want_fine=True)
+    fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5]), E[0], E[-1])
+    assert np.max(np.abs(fine - ref["fine"][0])) <= 1e-11 * ref["fine"][0].max()

@@ -235,7 +235,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
     if ((rc = t->counter.ensure(sizeof(unsigned long long) * 4096))) return rc;
     if ((rc = t->lims.ensure(sizeof(double) * 2))) return rc;
     if (conv) {
-        if ((rc = t->conv_grid.ensure(sizeof(double) * kConvN))) return rc;
+        if ((rc = t->conv_grid.ensure(sizeof(double) * 3 * kConvN))) return rc;  // grid | bin widths | reciprocals
         if ((rc = t->conv_avg.ensure(sizeof(double) * (size_t)n_flux))) return rc;
     }
     const long long chunk = std::max<long long>(1, std::min<long long>(t->chunk, B));
@@ -251,6 +251,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         sa.is_conv = conv ? 1 : 0;
         sa.conv_grid = (double*)t->conv_grid.p;
         sa.conv_avg = (double*)t->conv_avg.p;
+        sa.conv_bw = (double*)t->conv_grid.p + kConvN;
+        sa.conv_ybw = (double*)t->conv_grid.p + 2 * kConvN;
         k_setup<T><<<1, 128, 0, st>>>(sa, cc_ptr<T>(t));
         KLP_CUDA(cudaGetLastError());
     }
@@ -307,6 +309,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             TimedLaunch tl(t, st, 3);
             ConvArgs ca;
             ca.g = (const double*)t->conv_grid.p;
+            ca.bw = (const double*)t->conv_grid.p + kConvN;
+            ca.ybw = (const double*)t->conv_grid.p + 2 * kConvN;
             ca.prof = (const double*)t->prof.p;
             ca.prof_stride = kConvN - 1;
             ca.x = d_energy;
@@ -318,7 +322,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             dim3 grid((unsigned)((n_flux + kConvThreads - 1) / kConvThreads), (unsigned)nb);
             // gridDim.y limit is 65535
             if (nb > 65535) return fail(KLP_ERR_ARG, "chunk must be <= 65535 for convolution models");
-            k_conv<<<grid, kConvThreads, 0, st>>>(ca);
+            KLP_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+            k_conv<<<grid, kConvThreads, kConvSmemBytes, st>>>(ca);
             KLP_CUDA(cudaGetLastError());
         }
     }

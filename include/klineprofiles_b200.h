@@ -67,8 +67,12 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
                      const float* radii, const float* gmin, const float* gmax, const float* upper,
                      const float* lower, int device, klp_table** out);
 
-/* Load a table file: the flat ".klpt" container written by lineprofiles_b200.tableio.save_table
- * (see that file for the layout). */
+/* Load a table file.  Two formats, told apart by their magic:
+ *  - FITS with the reference's schema (io.zig:8-87): HDU 2 column 1 spins, HDU 3 column 1
+ *    cos(inclination), HDU 4.. one BINTABLE per (a, mu) frame with columns r, gmin, gmax,
+ *    upper_f[n_g], lower_f[n_g] (E or D) -- i.e. the shipped kerr-transfer-functions.fits;
+ *    read by a dependency-free reader (no cfitsio);
+ *  - the flat ".klpt" container written by lineprofiles_b200.tableio.save_table. */
 int klp_table_load(const char* path, int device, klp_table** out);
 
 void klp_table_destroy(klp_table* t);
@@ -149,7 +153,8 @@ int klp_fma_peak_gflops(klp_table* t, int precision, double* gflops);
  *        double* flux_variance  unused, never touched,
  *        const char* init       unused)
  * Process-global state like the reference (xspec-wrapper.zig:57-68): on first use the table is
- * loaded from $KLINE_PROF_DATA_DIR (default ".") -- "kerr-transfer-functions.klpt" -- or from the
+ * loaded from $KLINE_PROF_DATA_DIR (default ".") -- "kerr-transfer-functions.fits" as in the reference
+ * (xspec-wrapper.zig:10-11), else "kerr-transfer-functions.klpt" -- or from the
  * table installed with klp_set_default_table().  Errors: message on stderr prefixed
  * "kerrlineprofile: ", "MODEL OUTPUT SET TO ZERO", flux zero-filled (xspec-wrapper.zig:361-372).
  * The radial-grid limit ratchet of the reference (limits only shrink across calls,

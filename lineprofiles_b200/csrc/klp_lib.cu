@@ -539,6 +539,164 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     return KLP_OK;
 }
 
+// ---- FITS reader for the reference's table schema (io.zig:8-87; cfitsio is not available, so this is
+// a dependency-free reader of exactly what readFitsFile touches): HDU 2 column 1 = spins, HDU 3
+// column 1 = cos(inclination), HDU 4.. = one BINTABLE per (a, mu) frame with columns
+// 1 r, 2 gmin, 3 gmax, 4 upper_f[n_g], 5 lower_f[n_g] (HDU and column numbers 1-based as in cfitsio).
+namespace {
+struct FitsCol { char type; long repeat; size_t offset, width; };
+struct FitsHdu {
+    bool bintable = false;
+    long naxis1 = 0, naxis2 = 0;
+    size_t data_off = 0, data_bytes = 0;
+    std::vector<FitsCol> cols;
+};
+
+bool fits_parse(FILE* f, std::vector<FitsHdu>& hdus, std::string& err) {
+    std::fseek(f, 0, SEEK_END);
+    const long fsize = std::ftell(f);
+    long pos = 0;
+    char card[81];
+    card[80] = 0;
+    while (pos + 2880 <= fsize) {
+        FitsHdu h;
+        long bitpix = 8, naxis = 0, pcount = 0, gcount = 1, tfields = 0;
+        std::vector<long> naxes;
+        std::vector<std::string> tform;
+        bool end = false, first = true;
+        while (!end) {
+            if (pos + 2880 > fsize) { err = "truncated FITS header"; return false; }
+            std::fseek(f, pos, SEEK_SET);
+            for (int c = 0; c < 36; ++c) {
+                if (std::fread(card, 1, 80, f) != 80) { err = "short read in FITS header"; return false; }
+                std::string key(card, 8);
+                while (!key.empty() && key.back() == ' ') key.pop_back();
+                std::string val(card + 10, 70);
+                if (first) {
+                    first = false;
+                    if (hdus.empty()) { if (key != "SIMPLE") { err = "not a FITS file"; return false; } }
+                    else if (key != "XTENSION") { err = "bad FITS extension header"; return false; }
+                    if (key == "XTENSION") h.bintable = val.find("BINTABLE") != std::string::npos;
+                }
+                if (key == "END") { end = true; continue; }
+                if (end || card[8] != '=') continue;
+                auto num = [&]() { return std::strtol(val.c_str(), nullptr, 10); };
+                auto str = [&]() {
+                    size_t a = val.find('\''), b = val.find('\'', a + 1);
+                    std::string v = (a == std::string::npos || b == std::string::npos) ? std::string() : val.substr(a + 1, b - a - 1);
+                    while (!v.empty() && v.back() == ' ') v.pop_back();
+                    return v;
+                };
+                if (key == "BITPIX") bitpix = num();
+                else if (key == "NAXIS") { naxis = num(); naxes.assign((size_t)std::max(0l, naxis), 0); }
+                else if (key == "PCOUNT") pcount = num();
+                else if (key == "GCOUNT") gcount = num();
+                else if (key == "TFIELDS") { tfields = num(); tform.assign((size_t)std::max(0l, tfields), ""); }
+                else if (key.compare(0, 5, "NAXIS") == 0 && key.size() > 5) {
+                    long k = std::strtol(key.c_str() + 5, nullptr, 10);
+                    if (k >= 1 && k <= (long)naxes.size()) naxes[k - 1] = num();
+                } else if (key.compare(0, 5, "TFORM") == 0) {
+                    long k = std::strtol(key.c_str() + 5, nullptr, 10);
+                    if (k >= 1 && k <= (long)tform.size()) tform[k - 1] = str();
+                }
+            }
+            pos += 2880;
+        }
+        size_t nelem = naxes.empty() ? 0 : 1;
+        for (long n : naxes) nelem *= (size_t)n;
+        h.data_off = (size_t)pos;
+        h.data_bytes = (size_t)(std::labs(bitpix) / 8) * (size_t)gcount * ((size_t)pcount + nelem);
+        if (h.bintable) {
+            if (naxes.size() != 2) { err = "BINTABLE without NAXIS=2"; return false; }
+            h.naxis1 = naxes[0];
+            h.naxis2 = naxes[1];
+            size_t off = 0;
+            for (auto& tf : tform) {
+                char* endp = nullptr;
+                long rep = std::strtol(tf.c_str(), &endp, 10);
+                if (endp == tf.c_str()) rep = 1;
+                const char ty = *endp;
+                size_t w = ty == 'E' || ty == 'J' ? 4 : ty == 'D' || ty == 'K' ? 8 : ty == 'I' ? 2 : ty == 'B' || ty == 'L' || ty == 'A' ? 1 : 0;
+                if (!w) { err = "unsupported TFORM '" + tf + "'"; return false; }
+                h.cols.push_back({ty, rep, off, w});
+                off += w * (size_t)rep;
+            }
+            if ((long)off != h.naxis1) { err = "TFORM widths do not add up to NAXIS1"; return false; }
+        }
+        pos += (long)((h.data_bytes + 2879) / 2880 * 2880);
+        hdus.push_back(h);
+    }
+    return true;
+}
+
+// column `col` (0-based) of a BINTABLE as floats, rows x repeat
+bool fits_column(FILE* f, const FitsHdu& h, size_t col, std::vector<float>& out, long& repeat, std::string& err) {
+    if (!h.bintable || col >= h.cols.size()) { err = "missing table column"; return false; }
+    const FitsCol& c = h.cols[col];
+    if (c.type != 'E' && c.type != 'D') { err = "table column is not floating point"; return false; }
+    repeat = c.repeat;
+    std::vector<unsigned char> raw((size_t)h.naxis1 * (size_t)h.naxis2);
+    std::fseek(f, (long)h.data_off, SEEK_SET);
+    if (std::fread(raw.data(), 1, raw.size(), f) != raw.size()) { err = "truncated FITS table data"; return false; }
+    out.resize((size_t)h.naxis2 * (size_t)c.repeat);
+    for (long r = 0; r < h.naxis2; ++r)
+        for (long k = 0; k < c.repeat; ++k) {
+            const unsigned char* p = raw.data() + (size_t)r * h.naxis1 + c.offset + (size_t)k * c.width;
+            if (c.type == 'E') {
+                uint32_t u = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+                float v;
+                std::memcpy(&v, &u, 4);
+                out[(size_t)r * c.repeat + k] = v;
+            } else {
+                uint64_t u = 0;
+                for (int b = 0; b < 8; ++b) u = (u << 8) | p[b];
+                double v;
+                std::memcpy(&v, &u, 8);
+                out[(size_t)r * c.repeat + k] = (float)v;
+            }
+        }
+    return true;
+}
+
+int load_fits_table(const char* path, int device, klp_table** out) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(KLP_ERR_IO, std::string("cannot open table file: ") + path);
+    std::vector<FitsHdu> hdus;
+    std::string err;
+    auto bad = [&](const std::string& m) { std::fclose(f); return fail(KLP_ERR_IO, std::string(path) + ": " + m); };
+    if (!fits_parse(f, hdus, err)) return bad(err);
+    if (hdus.size() < 4) return bad("expected spins (HDU 2), inclinations (HDU 3) and at least one frame (HDU 4..)");
+    std::vector<float> spins, mus, col;
+    long rep = 0;
+    if (!fits_column(f, hdus[1], 0, spins, rep, err) || rep != 1) return bad("HDU 2: " + err);
+    if (!fits_column(f, hdus[2], 0, mus, rep, err) || rep != 1) return bad("HDU 3: " + err);
+    const size_t F = hdus.size() - 3;
+    if (F != spins.size() * mus.size()) return bad("number of frame HDUs != n_spins * n_inclinations");
+    const long n_r = hdus[3].naxis2;
+    long n_g = 0;
+    std::vector<float> radii, gmin, gmax, upper, lower;
+    for (size_t fr = 0; fr < F; ++fr) {
+        const FitsHdu& h = hdus[3 + fr];
+        if (h.naxis2 != n_r) return bad("frames have different numbers of radii");
+        std::vector<float>* dst3[3] = {&radii, &gmin, &gmax};
+        for (int c = 0; c < 3; ++c) {
+            if (!fits_column(f, h, (size_t)c, col, rep, err) || rep != 1) return bad("frame column: " + err);
+            dst3[c]->insert(dst3[c]->end(), col.begin(), col.end());
+        }
+        std::vector<float>* dst2[2] = {&upper, &lower};
+        for (int c = 0; c < 2; ++c) {
+            if (!fits_column(f, h, (size_t)(3 + c), col, rep, err)) return bad("frame branch column: " + err);
+            if (fr == 0 && c == 0) n_g = rep;
+            if (rep != n_g) return bad("frames have different numbers of g* knots");
+            dst2[c]->insert(dst2[c]->end(), col.begin(), col.end());
+        }
+    }
+    std::fclose(f);
+    return klp_table_create(spins.data(), (int)spins.size(), mus.data(), (int)mus.size(), (int)n_r, (int)n_g, radii.data(),
+                            gmin.data(), gmax.data(), upper.data(), lower.data(), device, out);
+}
+}  // namespace
+
 int klp_table_load(const char* path, int device, klp_table** out) {
     if (!out) return fail(KLP_ERR_ARG, "null out");
     *out = nullptr;
@@ -547,9 +705,14 @@ int klp_table_load(const char* path, int device, klp_table** out) {
     if (!f) return fail(KLP_ERR_IO, std::string("cannot open table file: ") + path);
     char magic[8];
     int32_t d[4];
+    if (std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "SIMPLE  ", 8) == 0) {
+        std::fclose(f);
+        return load_fits_table(path, device, out);
+    }
+    std::fseek(f, 0, SEEK_SET);
     if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "KLPT0001", 8) != 0 || std::fread(d, 4, 4, f) != 4) {
         std::fclose(f);
-        return fail(KLP_ERR_IO, std::string("not a KLPT0001 table: ") + path);
+        return fail(KLP_ERR_IO, std::string("neither a FITS nor a KLPT0001 table: ") + path);
     }
     const int n_a = d[0], n_mu = d[1], n_r = d[2], n_g = d[3];
     if (n_a < 1 || n_mu < 1 || n_r < 3 || n_g < 2 || n_g > kMaxNG) { std::fclose(f); return fail(KLP_ERR_IO, "bad table dimensions in file"); }
@@ -811,7 +974,8 @@ int klp_fma_peak_gflops(klp_table* t, int precision, double* gflops) {
 namespace {
 const char* kMsgPrefix = "kerrlineprofile: ";              // xspec-wrapper.zig:12
 const char* kDataDirEnv = "KLINE_PROF_DATA_DIR";           // xspec-wrapper.zig:10
-const char* kModelFile = "kerr-transfer-functions.klpt";   // flat-container twin of xspec-wrapper.zig:11
+const char* kModelFile = "kerr-transfer-functions.fits";   // MODELPATH, xspec-wrapper.zig:11
+const char* kModelFileFlat = "kerr-transfer-functions.klpt"; // flat-container twin (lineprofiles_b200/tableio.py)
 std::mutex g_legacy_mu;
 klp_table* g_default_table = nullptr;  // installed by the caller
 klp_table* g_owned_table = nullptr;    // lazily loaded singleton (xspec-wrapper.zig:61)
@@ -826,6 +990,8 @@ int legacy_table(klp_table** out) {
         std::string path = std::string(root ? root : ".") + "/" + kModelFile;  // getModelPath, :30-48
         int dev = 0;
         if (const char* d = std::getenv("KLINE_PROF_DEVICE")) dev = std::atoi(d);
+        if (FILE* probe = std::fopen(path.c_str(), "rb")) std::fclose(probe);
+        else path = std::string(root ? root : ".") + "/" + kModelFileFlat;
         int rc = klp_table_load(path.c_str(), dev, &g_owned_table);
         if (rc) return rc;
     }

@@ -91,3 +91,25 @@ def test_xspec_symbols_zero_fill_on_error(tmp_path, capfd, monkeypatch):
     err = capfd.readouterr().err
     assert np.all(flux == 0)
     assert "kerrlineprofile: " in err and "MODEL OUTPUT SET TO ZERO" in err and "KLINE_PROF_DATA_DIR" in err
+
+
+def test_fits_table_in_reference_schema(tmp_path):
+    """klp_table_load reads the reference's FITS layout (io.zig:8-87: HDU2 spins, HDU3 cos-inclinations,
+    HDU4.. one BINTABLE per frame with r, gmin, gmax, upper_f[30], lower_f[30]) without cfitsio."""
+    small = syn.make_table(5, 4, 11, 30)
+    p = str(tmp_path / "kerr-transfer-functions.fits")
+    tableio.save_fits(p, small)
+    t = klp.Table.load(p, device=-1)
+    assert (t.n_a, t.n_mu, t.n_r, t.n_g) == (5, 4, 11, 30)
+    for a, mu in ((0.3, 0.5), (0.9, 0.1), (2.0, 2.0)):
+        want = [0, 0]
+        ia = np.nonzero(small["spins"] >= np.float32(a))[0]
+        im = np.nonzero(small["mus"] >= np.float32(mu))[0]
+        want = [int(ia[0]) if ia.size else 0, int(im[0]) if im.size else 0]
+        assert t.find_parameter_indices(a, mu) == want
+    t.close()
+    # one frame short -> rejected
+    raw = open(p, "rb").read()
+    (tmp_path / "short.fits").write_bytes(raw[: len(raw) - 2880 * 2])
+    with pytest.raises(klp.KlpError):
+        klp.Table.load(str(tmp_path / "short.fits"), device=-1)

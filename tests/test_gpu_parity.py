@@ -306,3 +306,14 @@ def test_conv_linearity_config3_grid(gpu_table):
     c2 = gpu_table.eval_batch("kconv", p, E, spectrum=s2, precision="f32")
     c3 = gpu_table.eval_batch("kconv", p, E, spectrum=3.0 * s1 + s2, precision="f32")
     np.testing.assert_allclose(c3, 3.0 * c1 + c2, rtol=1e-9, atol=1e-18)
+
+
+def test_fits_table_evaluates_like_arrays(tmp_path, gpu_table, table_arrays):
+    """The FITS route (reference schema) and the array route give the same table on the device."""
+    p = str(tmp_path / "kerr-transfer-functions.fits")
+    tableio.save_fits(p, table_arrays)
+    t2 = klp.Table.load(p, 0)
+    E = syn.energy_grid_linear(200)
+    q = syn.random_params("kline5", 5, seed=4)
+    assert np.array_equal(t2.eval_batch("kline5", q, E), gpu_table.eval_batch("kline5", q, E))
+    t2.close()

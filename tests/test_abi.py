@@ -113,3 +113,20 @@ def test_fits_table_in_reference_schema(tmp_path):
     (tmp_path / "short.fits").write_bytes(raw[: len(raw) - 2880 * 2])
     with pytest.raises(klp.KlpError):
         klp.Table.load(str(tmp_path / "short.fits"), device=-1)
+
+
+def test_lmodel_matches_library():
+    """xspec/lmodel.dat (generated from lineprofiles_b200.xspec_models) binds c_<name> symbols the library exports
+    with the parameter counts the library expects; layout as reference xspec/lmodel.dat:1-59."""
+    from lineprofiles_b200 import xspec_models as xm
+    lib = klp.load_library()
+    text = xm.lmodel_text()   # what xspec/make_lmodel.py writes to xspec/lmodel.dat at build time
+    heads = [ln.split() for ln in text.splitlines() if "c_k" in ln]
+    assert [h[0] for h in heads] == ["kline", "kline5", "kconv", "kconv5", "kconv10"]
+    for h in heads:
+        name, npar, func, kind = h[0], int(h[1]), h[4], h[5]
+        assert func == "c_" + name and hasattr(lib, name)
+        assert npar == lib.klp_model_nparams(klp.MODELS[name]) == len(xm.MODELS[name][1])
+        assert kind == ("con" if name.startswith("kconv") else "add")
+    assert [p[0] for p in xm.MODELS["kline5"][1]][:7] == ["a", "incl", "eline", "rmin", "rmax", "rcut", "alpha"]
+    assert [p[0] for p in xm.MODELS["kconv"][1]] == ["a", "incl", "rmin", "rmax", "alpha"]

@@ -271,8 +271,13 @@ def main():
         sets_per_launch = B / max(quad_launches, 1)
         avg_launch_ms = quad_ms / max(quad_launches, 1)
         achieved = bytes_per_set * sets_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else None
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled per launch
+        tp = os.path.join(ROOT, "profiles", "r01_quad_traffic.json")
+        if os.path.exists(tp) and prec == "f32":
+            tj = json.load(open(tp))
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * sets_per_launch / tj["sets_per_launch"]
         roofline = {"bound": "hbm", "kernel": "k_quad", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_spectrum": bytes_per_set, "avg_launch_ms": avg_launch_ms,
                     "sets_per_launch": sets_per_launch,
                     "note": "the quadrature is FP-issue bound, not HBM bound (SURVEY.md §8d); see roofline_compute"}

@@ -291,6 +291,17 @@ def main():
                            "gather": "one NCCL all_gather_into_tensor of the spectra per step" if world > 1 else "none (1 GPU)",
                            "l2": "256 MiB buffer zeroed between steps (L2 flush) and a fresh parameter batch every step"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if traffic is not None and clocks and clocks.get("sm_mhz"):
+            # the bound that applies: warp-instruction issue slots (4 per SM per clock); instructions per spectrum
+            # from the ncu capture, rate from this run
+            wi = tj["warp_instructions_per_set"]
+            peak_issue = 4.0 * torch.cuda.get_device_properties(dev).multi_processor_count * clocks["sm_mhz"] * 1e6
+            ach_issue = wi * sets_per_launch / (avg_launch_ms * 1e-3)
+            line["roofline_issue"] = {"bound": "warp_instruction_issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
+                                      "unit": "G warp-inst/s", "frac": ach_issue / peak_issue,
+                                      "warp_instructions_per_spectrum": wi,
+                                      "source": "profiles/r01_quad_traffic.json (ncu smsp__inst_executed.sum) x measured launch rate; "
+                                                "peak = 4 x SMs x sm clock sampled during the run"}
         try:
             pk = gt.fma_peak_gflops(prec)
         except Exception:

@@ -197,7 +197,7 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cuda
 
 template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
     int nt = t->quad_threads;
-    if (nt <= 0) nt = sizeof(T) == 4 ? 512 : 1024;
+    if (nt <= 0) nt = 512;
     switch (nt) {
         case 128: return launch_quad_nt<T, 128>(t, q, st);
         case 256: return launch_quad_nt<T, 256>(t, q, st);

@@ -28,7 +28,8 @@ class KlpError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libklineprofiles_b200.so")
+    # KLP_LIBRARY: developer override to A/B-test differently compiled builds of the same library
+    return os.environ.get("KLP_LIBRARY") or os.path.join(_HERE, "libklineprofiles_b200.so")
 
 
 def load_library():

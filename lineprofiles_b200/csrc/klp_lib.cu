@@ -273,6 +273,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.fine = (T*)t->fine.p;
         q.scratch = nullptr;
         q.allow_fast = (t->fast_ok && t->use_fast) ? 1 : 0;
+        q.one = 1.0f;
         q.counter = (unsigned long long*)t->counter.p + c;
         q.use_limits = ex.use_limits ? 1 : 0;
         q.lim_lo = (T)ex.lim_lo;

@@ -128,8 +128,10 @@ int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d
 int klp_set_timing(klp_table* t, int enable);
 int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 
-/* Tuning knobs (testing / benchmarking): "quad_threads" (128..1024), "splits" (CTAs per set,
- * 0 = auto), "chunk" (sets per internal chunk), "fast" (1 = allow the branch-free exact-arithmetic
+/* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default), "splits" (CTAs
+ * per set, 0 = auto), "team_mode" (0 = auto, 1 = teams of 4 warps share a chain of radii, 2 = the whole CTA
+ * is one team: the latency mode chosen automatically for very small batches), "chunk" (sets per internal
+ * chunk), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);

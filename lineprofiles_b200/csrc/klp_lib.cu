@@ -120,6 +120,8 @@ struct klp_table {
     bool fast_ok = false;  // table values within the binades that license the FAST arithmetic (klp_kernels.cuh)
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
+    int team_mode = 0;     // 0 = auto, 1 = teams of kTeam warps, 2 = whole-CTA team
+    int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
     long chunk = 65535;
     // timing
     bool timing = false;
@@ -162,9 +164,10 @@ template <> CallConsts<float>* cc_ptr<float>(klp_table* t) { return (CallConsts<
 template <> CallConsts<double>* cc_ptr<double>(klp_table* t) { return (CallConsts<double>*)t->cc64.p; }
 
 template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, QuadArgs<T>& q, size_t smem, size_t fb, cudaStream_t st) {
-    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM>, NT, smem));
+    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM, false>, NT, smem));
     if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
@@ -181,7 +184,10 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         if (rc) return rc;
         q.scratch = (T*)t->scratch.p;
     }
-    k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
+    // latency mode: every CTA gets at most one group of a set -> the whole CTA walks that group's radii as one team
+    const bool whole = t->team_mode == 2 || (t->team_mode == 0 && splits >= 16);
+    if (whole) k_quad<T, NT, FRAME_SMEM, true><<<grid, NT, smem, st>>>(q);
+    else k_quad<T, NT, FRAME_SMEM, false><<<grid, NT, smem, st>>>(q);
     KLP_CUDA(cudaGetLastError());
     return KLP_OK;
 }
@@ -199,13 +205,11 @@ template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st
     int nt = t->quad_threads;
     if (nt <= 0) nt = 512;
     switch (nt) {
-        case 128: return launch_quad_nt<T, 128>(t, q, st);
         case 256: return launch_quad_nt<T, 256>(t, q, st);
-        case 384: return launch_quad_nt<T, 384>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);
         case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
-    return fail(KLP_ERR_ARG, "quad_threads must be 128, 256, 384, 512 or 1024");
+    return fail(KLP_ERR_ARG, "quad_threads must be 256, 512 or 1024");
 }
 
 TableDev table_dev(const klp_table* t) {
@@ -323,8 +327,14 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             dim3 grid((unsigned)((n_flux + kConvThreads - 1) / kConvThreads), (unsigned)nb);
             // gridDim.y limit is 65535
             if (nb > 65535) return fail(KLP_ERR_ARG, "chunk must be <= 65535 for convolution models");
-            KLP_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
-            k_conv<<<grid, kConvThreads, kConvSmemBytes, st>>>(ca);
+            if (t->conv_mode == 1) {
+                dim3 gridf((unsigned)((n_flux + kConvFastBinsPerCta - 1) / kConvFastBinsPerCta), (unsigned)nb);
+                KLP_CUDA(cudaFuncSetAttribute(k_conv_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvFastSmemBytes));
+                k_conv_fast<<<gridf, kConvFastThreads, kConvFastSmemBytes, st>>>(ca);
+            } else {
+                KLP_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+                k_conv<<<grid, kConvThreads, kConvSmemBytes, st>>>(ca);
+            }
             KLP_CUDA(cudaGetLastError());
         }
     }
@@ -906,11 +916,17 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
     std::string k(key);
     if (k == "quad_threads") {
-        if (value != 0 && value != 128 && value != 256 && value != 384 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
+        if (value != 0 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
         t->quad_threads = (int)value;
     } else if (k == "splits") {
         if (value < 0 || value > kNGroups) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "conv_mode") {
+        if (value < 0 || value > 1) return fail(KLP_ERR_ARG, "conv_mode");
+        t->conv_mode = (int)value;
+    } else if (k == "team_mode") {
+        if (value < 0 || value > 2) return fail(KLP_ERR_ARG, "team_mode");
+        t->team_mode = (int)value;
     } else if (k == "fast") {
         t->use_fast = value != 0;
     } else if (k == "chunk") {

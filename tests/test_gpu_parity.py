@@ -185,12 +185,12 @@ def test_invariance_to_batching_knobs(gpu_table):
     perm = np.random.default_rng(0).permutation(700)
     assert np.array_equal(gpu_table.eval_batch("kline5", p[perm], E, precision="f32"), base[perm])
     try:
-        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 128), ("quad_threads", 512)):
+        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("team_mode", 1), ("team_mode", 2)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
-            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0}[key])
+            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "team_mode": 0}[key])
     finally:
-        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0)):
+        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0), ("team_mode", 0)):
             gpu_table.set_option(key, val)
 
 
@@ -306,6 +306,34 @@ def test_conv_linearity_config3_grid(gpu_table):
     c2 = gpu_table.eval_batch("kconv", p, E, spectrum=s2, precision="f32")
     c3 = gpu_table.eval_batch("kconv", p, E, spectrum=3.0 * s1 + s2, precision="f32")
     np.testing.assert_allclose(c3, 3.0 * c1 + c2, rtol=1e-9, atol=1e-18)
+
+
+def test_conv_mode_cumulative_profile(gpu_table, oracle_table):
+    """Option "conv_mode" = 1 (cumulative-profile formulation of convolution.zig:58-102, a different operation
+    order): within 1e-9 relative + 1e-12 of the peak of the reference-order result on linear, log and ragged grids,
+    shared and per-set spectra, and against the oracle at the BASELINE tolerance."""
+    cases = [("kconv", syn.energy_grid_log(4096), 6), ("kconv10", syn.energy_grid_log(300), 5),
+             ("kconv5", syn.energy_grid_linear(1000), 5), ("kconv", syn.energy_grid_linear(7), 3),
+             ("kconv", syn.energy_grid_linear(1), 2)]
+    try:
+        for model, E, nb in cases:
+            n = E.size - 1
+            spec = syn.powerlaw_continuum(E)
+            p = syn.random_params(model, nb, seed=20261 + n)
+            per_set = np.tile(spec, (nb, 1)) * np.linspace(0.5, 2.0, nb)[:, None]
+            for sp in (spec, per_set):
+                gpu_table.set_option("conv_mode", 0)
+                exact = gpu_table.eval_batch(model, p, E, spectrum=sp, precision="f32")
+                gpu_table.set_option("conv_mode", 1)
+                fast = gpu_table.eval_batch(model, p, E, spectrum=sp, precision="f32")
+                scale = np.max(np.abs(exact), axis=-1, keepdims=True)
+                err = np.abs(fast - exact) / (np.abs(exact) + 1e-3 * scale)
+                assert np.max(err) < 1e-9, (model, n, float(np.max(err)))
+            want = oracle_table.eval_batch(model, p, E, spectrum=spec, precision="f32", threads=4)["out"]
+            gpu_table.set_option("conv_mode", 1)
+            assert_parity(gpu_table.eval_batch(model, p, E, spectrum=spec, precision="f32"), want, f"conv_mode 1 {model} n={n}")
+    finally:
+        gpu_table.set_option("conv_mode", 0)
 
 
 def test_fits_table_evaluates_like_arrays(tmp_path, gpu_table, table_arrays):

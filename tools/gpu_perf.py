@@ -40,7 +40,7 @@ if __name__ == "__main__":
     gt = klp.Table.from_arrays(tab, 0)
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
     print("fma peak GFLOP/s f32", gt.fma_peak_gflops("f32"), "f64", gt.fma_peak_gflops("f64"))
-    for nt in (128, 256, 384, 512, 1024):
+    for nt in (256, 512, 1024):
         run(gt, "kline5", B, "f32", opts={"quad_threads": nt})
     for nt in (256, 512, 1024):
         run(gt, "kline5", B // 2, "f64", opts={"quad_threads": nt})

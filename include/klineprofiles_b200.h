@@ -129,9 +129,9 @@ int klp_set_timing(klp_table* t, int enable);
 int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 
 /* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default), "splits" (CTAs
- * per set, 0 = auto), "team_mode" (0 = auto, 1 = teams of 4 warps share a chain of radii, 2 = the whole CTA
- * is one team: the latency mode chosen automatically for very small batches), "chunk" (sets per internal
- * chunk), "fast" (1 = allow the branch-free exact-arithmetic
+ * that share one set, 0 = auto: more than one only when the batch is smaller than the GPU), "conv_mode" (0 = the
+ * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
+ * faster, equal to rounding), "chunk" (sets per internal chunk), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);

@@ -109,7 +109,7 @@ struct klp_table {
     int sm_count = 0;
     int max_smem_optin = 0;
     // workspaces
-    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims;
+    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done;
     // host-API staging
     Buf d_energy, d_spec, d_params[2], d_out[2], d_spec_slot[2];
     PinBuf h_params[2], h_out[2], h_spec_slot[2];
@@ -120,7 +120,6 @@ struct klp_table {
     bool fast_ok = false;  // table values within the binades that license the FAST arithmetic (klp_kernels.cuh)
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
-    int team_mode = 0;     // 0 = auto, 1 = teams of kTeam warps, 2 = whole-CTA team
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
     long chunk = 65535;
     // timing
@@ -164,18 +163,17 @@ template <> CallConsts<float>* cc_ptr<float>(klp_table* t) { return (CallConsts<
 template <> CallConsts<double>* cc_ptr<double>(klp_table* t) { return (CallConsts<double>*)t->cc64.p; }
 
 template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, QuadArgs<T>& q, size_t smem, size_t fb, cudaStream_t st) {
-    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM, false>, NT, smem));
+    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM>, NT, smem));
     if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
     if (splits <= 0) {
         splits = 1;
-        if (q.B < resident) splits = (int)std::min<long long>(kNGroups, (resident + q.B - 1) / q.B);
+        if (q.B < resident) splits = (int)std::min<long long>(kMaxSplits, (resident + q.B - 1) / q.B);
     }
-    splits = std::max(1, std::min(splits, kNGroups));
+    splits = std::max(1, std::min(splits, kMaxSplits));
     q.splits = splits;
     const long long items = q.B * splits;
     const int grid = (int)std::min<long long>(items, resident);
@@ -184,10 +182,19 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         if (rc) return rc;
         q.scratch = (T*)t->scratch.p;
     }
-    // latency mode: every CTA gets at most one group of a set -> the whole CTA walks that group's radii as one team
-    const bool whole = t->team_mode == 2 || (t->team_mode == 0 && splits >= 16);
-    if (whole) k_quad<T, NT, FRAME_SMEM, true><<<grid, NT, smem, st>>>(q);
-    else k_quad<T, NT, FRAME_SMEM, false><<<grid, NT, smem, st>>>(q);
+    // deposit scratch: one region per CTA, or per set when a set is shared by several CTAs
+    q.vals_stride = (size_t)kNGroups * kRadial * 32;
+    const size_t regions = splits > 1 ? (size_t)q.B : (size_t)grid;
+    int rc = t->vals.ensure(regions * q.vals_stride * sizeof(T));
+    if (rc) return rc;
+    q.vals = (T*)t->vals.p;
+    q.done = nullptr;
+    if (splits > 1) {
+        if ((rc = t->done.ensure(sizeof(unsigned) * (size_t)q.B))) return rc;
+        KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * (size_t)q.B, st));
+        q.done = (unsigned*)t->done.p;
+    }
+    k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
     KLP_CUDA(cudaGetLastError());
     return KLP_OK;
 }
@@ -207,6 +214,9 @@ template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st
     switch (nt) {
         case 256: return launch_quad_nt<T, 256>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);
+#ifdef KLP_EXPERIMENT_NT
+        case KLP_EXPERIMENT_NT: return launch_quad_nt<T, KLP_EXPERIMENT_NT>(t, q, st);
+#endif
         case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
     return fail(KLP_ERR_ARG, "quad_threads must be 256, 512 or 1024");
@@ -754,7 +764,7 @@ void klp_table_destroy(klp_table* t) {
         if (t->d_frames) cudaFree(t->d_frames);
         if (t->d_spins) cudaFree(t->d_spins);
         if (t->d_mus) cudaFree(t->d_mus);
-        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims,
+        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done,
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})
             b->release();
@@ -916,17 +926,18 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
     std::string k(key);
     if (k == "quad_threads") {
+#ifdef KLP_EXPERIMENT_NT
+        if (value == KLP_EXPERIMENT_NT) { t->quad_threads = (int)value; return KLP_OK; }
+#endif
         if (value != 0 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
         t->quad_threads = (int)value;
     } else if (k == "splits") {
-        if (value < 0 || value > kNGroups) return fail(KLP_ERR_ARG, "splits");
+        if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
     } else if (k == "conv_mode") {
         if (value < 0 || value > 1) return fail(KLP_ERR_ARG, "conv_mode");
         t->conv_mode = (int)value;
-    } else if (k == "team_mode") {
-        if (value < 0 || value > 2) return fail(KLP_ERR_ARG, "team_mode");
-        t->team_mode = (int)value;
+
     } else if (k == "fast") {
         t->use_fast = value != 0;
     } else if (k == "chunk") {

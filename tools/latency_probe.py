@@ -10,8 +10,7 @@ gt = klp.Table.from_arrays(tab, 0)
 E = syn.energy_grid_linear(1000)
 El = syn.energy_grid_log(4096)
 spec = syn.powerlaw_continuum(El)
-for tm in (1, 2, 0):
-    gt.set_option("team_mode", tm)
+for tm in (0,):
     for model, B, en, sp in (("kline", 1, E, None), ("kline5", 1, E, None), ("kline5", 8, E, None), ("kline5", 64, E, None),
                              ("kline5", 296, E, None), ("kline5", 1000, E, None), ("kconv5", 1, El, spec)):
         p = syn.random_params(model, B, seed=3)

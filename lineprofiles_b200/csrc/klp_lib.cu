@@ -183,7 +183,7 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         q.scratch = (T*)t->scratch.p;
     }
     // deposit scratch: one region per CTA, or per set when a set is shared by several CTAs
-    q.vals_stride = (size_t)kNGroups * kRadial * kGroupBins;
+    q.vals_stride = (size_t)kRadial * kFineG;   // dense (radius, bin) addressing; only candidate bins are touched
     const size_t regions = splits > 1 ? (size_t)q.B : (size_t)grid;
     int rc = t->vals.ensure(regions * q.vals_stride * sizeof(T));
     if (rc) return rc;

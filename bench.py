@@ -302,6 +302,13 @@ def main():
                                       "warp_instructions_per_spectrum": wi,
                                       "source": "profiles/r01_quad_traffic.json (ncu smsp__inst_executed.sum) x measured launch rate; "
                                                 "peak = 4 x SMs x sm clock sampled during the run"}
+            if "fma_pipe_cycles_per_set" in tj:
+                # the bound that binds: cycles of the FP32 (FMA) datapath, one per sub-partition and clock
+                ach_pipe = tj["fma_pipe_cycles_per_set"] * sets_per_launch / (avg_launch_ms * 1e-3)
+                line["roofline_fp32_pipe"] = {"bound": "fp32_datapath_cycles", "achieved": ach_pipe / 1e9, "peak": peak_issue / 1e9,
+                                              "unit": "G pipe-cycles/s", "frac": ach_pipe / peak_issue,
+                                              "source": "profiles/r01_quad_traffic.json (ncu sm__pipe_fma_cycles_active) x measured launch rate"}
+            roofline["traffic_note"] = tj.get("note")
         try:
             pk = gt.fma_peak_gflops(prec)
         except Exception:

@@ -150,6 +150,14 @@ def main():
             tm = gt.get_timing()
             gt.set_timing(False)
             r[prec] = {"spectra_per_s": B / (ms * 1e-3), "ms": ms, "quad_ms": tm["quad"]["ms"], "conv_ms": tm["conv"]["ms"]}
+        # the cumulative-profile convolution (option conv_mode = 1: not the reference's operation order, equal to rounding)
+        gt.set_option("conv_mode", 1)
+        gt.set_timing(True)
+        ms = timed(lambda: device_eval(gt, "kconv", p, dE4k, 4096, out, spec=dspec, prec="f32"))
+        tm = gt.get_timing()
+        gt.set_timing(False)
+        gt.set_option("conv_mode", 0)
+        r["f32_conv_mode_1"] = {"spectra_per_s": B / (ms * 1e-3), "ms": ms, "quad_ms": tm["quad"]["ms"], "conv_ms": tm["conv"]["ms"]}
         cpu = cpu_rate(ot, "kconv", E4k, spec4k, max(cores(), 16)) if ot is not None else None
         emit({"config": 3, "what": f"kconv, batch of {B}, power-law continuum on the 4096-bin log grid", "gpu": r,
               "cpu_oracle_f32_spectra_per_s": cpu, "cpu_cores": cores()})
@@ -177,8 +185,12 @@ def main():
                 if WORLD > 1:
                     dist.all_gather_into_tensor(gathered, out)
         ms = timed(run, reps=1, warm=0 if B >= 100000 else 1)
+        gt.set_option("conv_mode", 1)
+        ms1 = timed(run, reps=1, warm=0)
+        gt.set_option("conv_mode", 0)
         emit({"config": 4, "what": f"kconv10, {B} walkers sharded x{WORLD}, 4096-bin grid, NCCL all-gather of the spectra per {chunk}-set chunk",
-              "gpu": {"f32": {"spectra_per_s": B / (ms * 1e-3), "ms": ms}}, "gathered_bytes_total": B * 4096 * 8 if WORLD > 1 else 0})
+              "gpu": {"f32": {"spectra_per_s": B / (ms * 1e-3), "ms": ms}, "f32_conv_mode_1": {"spectra_per_s": B / (ms1 * 1e-3), "ms": ms1}},
+              "gathered_bytes_total": B * 4096 * 8 if WORLD > 1 else 0})
 
     if 5 in cfgs:
         # table resolution sweep: fused kline throughput + stand-alone blend kernel GB/s

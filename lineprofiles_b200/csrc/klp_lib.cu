@@ -108,6 +108,7 @@ struct klp_table {
     float* d_mus = nullptr;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int max_smem_sm = 0;
     // workspaces
     Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done;
     // host-API staging
@@ -121,6 +122,7 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
     long chunk = 65535;
     // timing
     bool timing = false;
@@ -204,7 +206,14 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cuda
     const size_t fixed = QuadSmem<T>::fixed_bytes(t->n_g, NW);
     const size_t fb = QuadSmem<T>::frame_bytes(t->n_r, t->n_g);
     if (fixed > (size_t)t->max_smem_optin) return fail(KLP_ERR_ARG, "table rows too wide for shared memory");
-    if (fixed + fb <= (size_t)t->max_smem_optin) return launch_quad_impl<T, NT, true>(t, q, fixed + fb, fb, st);
+    // The blended frame lives in shared memory when that does not cost a resident CTA (f32: two 512-thread CTAs per SM are
+    // budgeted, see quad_min_blocks); otherwise in the per-CTA global scratch -- it is read once per radius (measured -0.7 %).
+    const int want = quad_min_blocks<T, NT>();
+    const size_t per_sm = (size_t)t->max_smem_sm;
+    const bool fits_one = fixed + fb <= (size_t)t->max_smem_optin;
+    const bool fits_want = (size_t)want * (fixed + fb + 1024) <= per_sm;
+    const bool global_helps = (size_t)want * (fixed + 1024) <= per_sm;
+    if (fits_one && !t->frame_global && (fits_want || !global_helps)) return launch_quad_impl<T, NT, true>(t, q, fixed + fb, fb, st);
     return launch_quad_impl<T, NT, false>(t, q, fixed, fb, st);
 }
 
@@ -521,6 +530,7 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete t; return fail(KLP_ERR_CUDA, "cudaGetDeviceProperties"); }
     t->sm_count = prop.multiProcessorCount;
     t->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    t->max_smem_sm = (int)prop.sharedMemPerMultiprocessor;
     auto bail = [&](int code, const std::string& m) { klp_table_destroy(t); return fail(code, m); };
     if (cudaMalloc(&t->d_frames, sizeof(float) * F * t->frame_stride) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(frames)");
     if (cudaMalloc(&t->d_spins, sizeof(float) * n_a) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(spins)");
@@ -934,6 +944,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "splits") {
         if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "frame_global") {
+        t->frame_global = value != 0;
     } else if (k == "conv_mode") {
         if (value < 0 || value > 1) return fail(KLP_ERR_ARG, "conv_mode");
         t->conv_mode = (int)value;

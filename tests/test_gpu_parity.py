@@ -142,6 +142,34 @@ def test_edge_parameters(gpu_table, oracle_table):
         assert_parity(got, want, f"edge params {prec}")
 
 
+def test_irregular_fine_grids(gpu_table, oracle_table):
+    """Sets whose fine grid in g is not an ascending finite sequence take the general path of the quadrature (every
+    bin a candidate, NaN-aware clamps): negative eline (descending grid), NaN eline, huge eline (all bins below gmin),
+    tiny eline (all above gmax, grid wider than a knot spacing)."""
+    E = syn.energy_grid_linear(300)
+    p = syn.random_params("kline5", 8, seed=77)
+    p[0, 2] = -6.4
+    p[1, 2] = np.nan
+    p[2, 2] = 1e6
+    p[3, 2] = 1e-3
+    p[4, 2] = 0.5         # bins ~13 times wider in g: wider than a knot spacing at some radii -> no node sharing
+    p[5, 2] = np.inf
+    for prec in ("f32", "f64"):
+        got = gpu_table.eval_batch("kline5", p, E, precision=prec)
+        want = oracle_table.eval_batch("kline5", p, E, precision=prec)["out"]
+        assert_parity(got, want, f"irregular grids {prec}")
+    # the options that move the blended frame / change the CTA shape must not change a bit
+    base = gpu_table.eval_batch("kline5", p, E, precision="f32")
+    try:
+        for key, val in (("frame_global", 1), ("quad_threads", 256), ("quad_threads", 1024)):
+            gpu_table.set_option(key, val)
+            assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base, equal_nan=True), (key, val)
+            gpu_table.set_option(key, 0)
+    finally:
+        gpu_table.set_option("frame_global", 0)
+        gpu_table.set_option("quad_threads", 0)
+
+
 @pytest.mark.parametrize("n_bins", [1, 2, 7, 100, 2500])
 def test_ragged_energy_grids(gpu_table, oracle_table, n_bins):
     rng = np.random.default_rng(n_bins)
@@ -185,12 +213,12 @@ def test_invariance_to_batching_knobs(gpu_table):
     perm = np.random.default_rng(0).permutation(700)
     assert np.array_equal(gpu_table.eval_batch("kline5", p[perm], E, precision="f32"), base[perm])
     try:
-        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("splits", 63), ("splits", 300)):
+        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
-            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0}[key])
+            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "frame_global": 0}[key])
     finally:
-        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0)):
+        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0), ("frame_global", 0)):
             gpu_table.set_option(key, val)
 
 

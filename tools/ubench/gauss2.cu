@@ -1,0 +1,60 @@
+// Microbenchmark: the product Gauss body with pair tables (gauss_share_pt) in isolation, and what-if variants selected by
+// compile-time experiment macros of klp_kernels.cuh (KLP_EXPERIMENT_NO_MUFU: approximations replaced by a multiply, wrong results).
+#include <cstdio>
+#include "../../lineprofiles_b200/csrc/klp_kernels.cuh"
+using namespace klp;
+
+__global__ void __launch_bounds__(512, 2) k(float* sink, int iters, float one, float dgv) {
+    __shared__ float4 s_knots[32];
+    __shared__ float s_gs[32];
+    __shared__ float4 s_rows[16 * 30];
+    __shared__ float4 s_kpair[4 * 30];
+    extern __shared__ float4 s_rpair[];   // [16][4 * 30]
+    const int n_g = 30, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto kn = [&](int k2, float& g0, float& d, float& y) {
+        if (k2 >= 2 && k2 < n_g) { const float gk = 5e-4f + k2 * (0.999f / 29), gp = 5e-4f + (k2 - 1) * (0.999f / 29); g0 = gp; d = gk - gp; y = 1.0f / d; }
+        else { g0 = 0.f; d = 1.f; y = 1.f; }
+    };
+    if (tid < n_g) {
+        float g0, d, y, g1, d1, y1;
+        kn(tid, g0, d, y); kn(tid + 1, g1, d1, y1);
+        s_gs[tid] = 5e-4f + tid * (0.999f / 29);
+        s_knots[tid] = make_float4(g0, d, y, 0.f);
+        s_kpair[2 * tid] = make_float4(g0, g0, d, d); s_kpair[2 * tid + 1] = make_float4(y, y, 0, 0);
+        s_kpair[2 * n_g + 2 * tid] = make_float4(g1, g0, d1, d); s_kpair[2 * n_g + 2 * tid + 1] = make_float4(y1, y, 0, 0);
+    }
+    for (int k2 = lane; k2 < n_g; k2 += 32) {
+        const float l0 = 1.0f + 0.01f * k2, dl = 0.01f, u0 = 0.8f + 0.01f * k2, du = 0.012f;
+        s_rows[warp * n_g + k2] = make_float4(l0, dl, u0, du);
+        float4* rp = s_rpair + warp * 4 * n_g;
+        rp[2 * k2] = make_float4(l0, l0, dl, dl); rp[2 * k2 + 1] = make_float4(u0, u0, du, du);
+        rp[2 * n_g + 2 * k2] = make_float4(l0 + 0.01f, l0, dl, dl); rp[2 * n_g + 2 * k2 + 1] = make_float4(u0 + 0.01f, u0, du, du);
+    }
+    __syncthreads();
+    RadCtx<float> c;
+    c.row = s_rows + warp * n_g; c.knots = s_knots; c.gq = nullptr; c.gs = s_gs; c.n_g = n_g;
+    c.est_inv_delta = 29.0f / 0.999f; c.est_off = -5e-4f * c.est_inv_delta + (0.5f - 2e-4f);
+    c.gmin = 0.3f; c.dg = dgv; c.ydg = 1.0f / dgv; c.tA = 0; c.tD = 10; c.one = one;
+    c.kpair = s_kpair; c.rpair = s_rpair + warp * 4 * n_g; c.pair_stride = 2 * n_g;
+    float acc = 0;
+    float glow = 0.35f + lane * 7.6e-4f;
+    for (int it = 0; it < iters; ++it) {
+        const float ghigh = glow + 7.6e-4f;
+        const float v = gauss_share_pt(c, glow, ghigh);
+        acc += v;
+        glow += 1e-7f * (v > 1e30f ? 1.f : 0.5f);
+    }
+    if (acc == -1.2345f) sink[0] = acc;
+}
+int main() {
+    float* sink; cudaMalloc(&sink, 4);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int iters = 2000, grid = p.multiProcessorCount * 2, smem = 16 * 4 * 30 * 16;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k<<<grid, 512, smem>>>(sink, 10, 1.0f, 0.6f);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0); k<<<grid, 512, smem>>>(sink, iters, 1.0f, 0.6f); cudaEventRecord(e1); cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("gauss_share_pt: %8.1f cycles per call per SMSP (8 warps resident)  %s\n", ms * 1e-3 * 1.965e9 / (8.0 * iters), cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}

@@ -172,8 +172,12 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
     if (splits <= 0) {
-        splits = 1;
-        if (q.B < resident) splits = (int)std::min<long long>(kMaxSplits, (resident + q.B - 1) / q.B);
+        // CTAs sharing a set.  Sets differ in cost by a factor of ~2, so a batch of the order of the resident CTAs is
+        // balanced by cutting every set into several (set, split) items (each split repeats the plan, ~3 % of a set);
+        // measured optimum (tools/splits_probe.py): ~8 items per resident CTA, at most 16 splits (32 for a handful of sets).
+        const long long want = (8 * resident + q.B - 1) / q.B;
+        const long long cap = q.B * 16 < resident ? 32 : 16;
+        splits = (int)std::max<long long>(1, std::min<long long>(want, cap));
     }
     splits = std::max(1, std::min(splits, kMaxSplits));
     q.splits = splits;

@@ -7,7 +7,7 @@ from lineprofiles_b200 import synthetic as syn
 gt = klp.Table.from_arrays(syn.make_table(), 0)
 E = syn.energy_grid_linear(1000)
 dE = torch.from_numpy(E).cuda()
-for B in (1, 8, 64):
+for B in (1, 8, 64, 148, 296, 592, 1000, 2960):
     p = syn.random_params("kline5", B, seed=3)
     dp = torch.from_numpy(p).cuda()
     out = torch.empty((B, 1000), dtype=torch.float64, device="cuda")

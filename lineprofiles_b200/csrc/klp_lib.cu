@@ -330,7 +330,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
                 r.out = d_out + (size_t)off * n_flux;
                 r.out_stride = (size_t)n_flux;
             }
-            k_rebin<T><<<(unsigned)nb, 128, 0, st>>>(r);
+            r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
+            k_rebin<T><<<(unsigned)nb, 256, sizeof(double) * (size_t)r.n_stage, st>>>(r);
             KLP_CUDA(cudaGetLastError());
         }
         if (conv && !stop_after_profile) {

@@ -122,6 +122,7 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
     long chunk = 65535;
     // timing
@@ -188,8 +189,10 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         if (rc) return rc;
         q.scratch = (T*)t->scratch.p;
     }
-    // deposit scratch: one region per CTA, or per set when a set is shared by several CTAs
-    q.vals_stride = (size_t)kRadial * kFineG;   // dense (radius, bin) addressing; only candidate bins are touched
+    // deposit scratch: a ring of kRingRadii radii per CTA when every set is owned by one CTA (it stays in L2), the whole
+    // (radius, bin) plane per set when sets are shared by several CTAs (small batches)
+    q.ring_mode = t->deposit_ring ? 1 : 0;
+    q.vals_stride = (size_t)((splits > 1 || !q.ring_mode) ? kRadial : kRingRadii) * kFineG;   // dense (radius, bin) addressing
     const size_t regions = splits > 1 ? (size_t)q.B : (size_t)grid;
     int rc = t->vals.ensure(regions * q.vals_stride * sizeof(T));
     if (rc) return rc;
@@ -949,6 +952,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "splits") {
         if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "deposit_ring") {
+        t->deposit_ring = value != 0;
     } else if (k == "frame_global") {
         t->frame_global = value != 0;
     } else if (k == "conv_mode") {

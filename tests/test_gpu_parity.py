@@ -171,7 +171,7 @@ def test_irregular_fine_grids(gpu_table, oracle_table):
         gpu_table.set_option("deposit_ring", 0)
 
 
-@pytest.mark.parametrize("n_bins", [1, 2, 7, 100, 2500])
+@pytest.mark.parametrize("n_bins", [1, 2, 7, 100, 2500, 5000])
 def test_ragged_energy_grids(gpu_table, oracle_table, n_bins):
     rng = np.random.default_rng(n_bins)
     E = np.sort(rng.uniform(0.3, 9.0, n_bins + 1))

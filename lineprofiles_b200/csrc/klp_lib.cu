@@ -122,6 +122,7 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    int stage_mb = 128;         // pinned staging per slot of the host pipeline (MB of output)
     bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
     long chunk = 65535;
@@ -425,9 +426,10 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         KLP_CUDA(cudaMemcpyAsync(t->d_spec.p, spectrum, sizeof(double) * (size_t)n_flux, cudaMemcpyHostToDevice, t->s_compute));
     }
     KLP_CUDA(cudaStreamSynchronize(t->s_compute));
-    // staging chunk: ~64 MB of output per slot
-    long long hc = (64ll << 20) / ((long long)n_flux * 8);
-    hc = std::max<long long>(256, std::min<long long>(hc, 16384));
+    // staging chunk: t->stage_mb of output per slot (two slots; default 128 MB).  Larger chunks amortise the idle tail of
+    // every k_quad launch, smaller ones shorten the last, un-overlapped copy-out.
+    long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
+    hc = std::max<long long>(256, std::min<long long>(hc, 65535));
     hc = std::min(hc, B);
     const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux;
     const size_t par_bytes = sizeof(double) * (size_t)hc * P;
@@ -952,6 +954,9 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "splits") {
         if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "stage_mb") {
+        if (value < 1 || value > 4096) return fail(KLP_ERR_ARG, "stage_mb");
+        t->stage_mb = (int)value;
     } else if (k == "deposit_ring") {
         t->deposit_ring = value != 0;
     } else if (k == "frame_global") {

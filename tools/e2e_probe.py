@@ -9,12 +9,12 @@ E = syn.energy_grid_linear(1000)
 B = 100000
 ps = [syn.random_params("kline5", B, seed=1000 + s) for s in range(3)]
 out = np.empty((B, 1000), np.float64)
-for chunk in (65535, 32768, 16384, 8192):
-    gt.set_option("chunk", chunk)
+for chunk in (32, 64, 128, 256, 512):
+    gt.set_option("stage_mb", chunk)
     gt.eval_batch("kline5", ps[0][:4096], E, precision="f32")
     gt.eval_batch("kline5", ps[0], E, precision="f32", out=out)
     t0 = time.perf_counter()
     for p in ps[1:]:
         gt.eval_batch("kline5", p, E, precision="f32", out=out)
     dt = (time.perf_counter() - t0) / 2
-    print(f"chunk {chunk:6d}: {B/dt:9.0f} spectra/s end to end", flush=True)
+    print(f"stage_mb {chunk:6d}: {B/dt:9.0f} spectra/s end to end", flush=True)

@@ -133,7 +133,7 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
  * faster, equal to rounding), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring and add them
  * while evaluating: no DRAM traffic, ~4.5 % slower; default 0), "chunk" (sets per internal chunk), "stage_mb" (pinned staging per slot of the
- * host-buffer pipeline, default 128), "fast" (1 = allow the branch-free exact-arithmetic
+ * host-buffer pipeline, default 128), "order" (1 = evaluate the costliest sets of a launch first (default), 0 = in input order), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);

@@ -110,7 +110,7 @@ struct klp_table {
     int max_smem_optin = 0;
     int max_smem_sm = 0;
     // workspaces
-    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done;
+    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done, order;
     // host-API staging
     Buf d_energy, d_spec, d_params[2], d_out[2], d_spec_slot[2];
     PinBuf h_params[2], h_out[2], h_spec_slot[2];
@@ -122,6 +122,7 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    bool use_order = true;      // evaluate the costliest sets of a launch first
     int stage_mb = 128;         // pinned staging per slot of the host pipeline (MB of output)
     bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
@@ -310,6 +311,14 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.lim_lo = (T)ex.lim_lo;
         q.lim_hi = (T)ex.lim_hi;
         q.lims_out = (ex.want_lims && c == 0) ? (T*)t->lims.p : nullptr;
+        q.order = nullptr;
+        if (nb >= 512 && t->use_order) {   // costliest sets first (k_order)
+            if ((rc = t->order.ensure(sizeof(int) * (size_t)nb))) return rc;
+            TimedLaunch tl(t, st, 0);   // accounted with the set-up kernels
+            k_order<<<1, 1024, 0, st>>>(q.params, P, (int)nb, (int*)t->order.p);
+            KLP_CUDA(cudaGetLastError());
+            q.order = (const int*)t->order.p;
+        }
         {
             TimedLaunch tl(t, st, 1);
             if ((rc = launch_quad<T>(t, q, st))) return rc;
@@ -784,7 +793,7 @@ void klp_table_destroy(klp_table* t) {
         if (t->d_frames) cudaFree(t->d_frames);
         if (t->d_spins) cudaFree(t->d_spins);
         if (t->d_mus) cudaFree(t->d_mus);
-        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done,
+        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done, &t->order,
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})
             b->release();
@@ -954,6 +963,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "splits") {
         if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
         t->splits = (int)value;
+    } else if (k == "order") {
+        t->use_order = value != 0;
     } else if (k == "stage_mb") {
         if (value < 1 || value > 4096) return fail(KLP_ERR_ARG, "stage_mb");
         t->stage_mb = (int)value;

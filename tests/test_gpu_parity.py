@@ -214,12 +214,12 @@ def test_invariance_to_batching_knobs(gpu_table):
     perm = np.random.default_rng(0).permutation(700)
     assert np.array_equal(gpu_table.eval_batch("kline5", p[perm], E, precision="f32"), base[perm])
     try:
-        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1), ("deposit_ring", 1)):
+        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1), ("deposit_ring", 1), ("order", 0)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
-            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0}[key])
+            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0, "order": 1}[key])
     finally:
-        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0)):
+        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0), ("order", 1)):
             gpu_table.set_option(key, val)
 
 

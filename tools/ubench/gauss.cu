@@ -254,7 +254,7 @@ template <int MODE> __global__ void __launch_bounds__(512, KLP_UB_MINB) k(float*
     soa.g0 = s_soa; soa.d = s_soa + 32; soa.y = s_soa + 64;
     soa.l0 = s_soa + 7 * 32 + warp * 128; soa.dl = soa.l0 + 32; soa.u0 = soa.l0 + 64; soa.du = soa.l0 + 96;
     RadCtx<float> c;
-    c.row = s_rows + warp * n_g; c.knots = s_knots; c.gq = nullptr; c.gs = s_gs; c.n_g = n_g;
+    c.row = s_rows + warp * n_g; c.knots = s_knots; c.gs = s_gs; c.n_g = n_g;
     c.est_inv_delta = 29.0f / 0.999f; c.est_off = -5e-4f * c.est_inv_delta + (0.5f - 2e-4f);
     c.gmin = 0.3f; c.dg = dgv; c.ydg = 1.0f / dgv; c.tA = 0; c.tD = 10; c.one = one;
     float acc = 0;

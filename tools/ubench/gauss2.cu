@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(512, 2) k(float* sink, int iters, float one, f
     }
     __syncthreads();
     RadCtx<float> c;
-    c.row = s_rows + warp * n_g; c.knots = s_knots; c.gq = nullptr; c.gs = s_gs; c.n_g = n_g;
+    c.row = s_rows + warp * n_g; c.knots = s_knots; c.gs = s_gs; c.n_g = n_g;
     c.est_inv_delta = 29.0f / 0.999f; c.est_off = -5e-4f * c.est_inv_delta + (0.5f - 2e-4f);
     c.gmin = 0.3f; c.dg = dgv; c.ydg = 1.0f / dgv; c.tA = 0; c.tD = 10; c.one = one;
     c.kpair = s_kpair; c.rpair = s_rpair + warp * 4 * n_g; c.pair_stride = 2 * n_g;

@@ -181,6 +181,7 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         const long long want = (8 * resident + q.B - 1) / q.B;
         const long long cap = q.B * 16 < resident ? 32 : 16;
         splits = (int)std::max<long long>(1, std::min<long long>(want, cap));
+        if (splits == 2) splits = 1;   // measured: two splits never pay for the repeated plan once the sets are cost-ordered
     }
     splits = std::max(1, std::min(splits, kMaxSplits));
     q.splits = splits;
@@ -195,14 +196,15 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     // (radius, bin) plane per set when sets are shared by several CTAs (small batches)
     q.ring_mode = t->deposit_ring ? 1 : 0;
     q.vals_stride = (size_t)((splits > 1 || !q.ring_mode) ? kRadial : kRingRadii) * kFineG;   // dense (radius, bin) addressing
-    const size_t regions = splits > 1 ? (size_t)q.B : (size_t)grid;
+    const size_t regions = splits > 1 ? (size_t)std::min<long long>(q.B, kSplitRegions) : (size_t)grid;
+    q.regions = (long long)regions;
     int rc = t->vals.ensure(regions * q.vals_stride * sizeof(T));
     if (rc) return rc;
     q.vals = (T*)t->vals.p;
     q.done = nullptr;
     if (splits > 1) {
-        if ((rc = t->done.ensure(sizeof(unsigned) * (size_t)q.B))) return rc;
-        KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * (size_t)q.B, st));
+        if ((rc = t->done.ensure(sizeof(unsigned) * 2 * (size_t)q.B))) return rc;
+        KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * 2 * (size_t)q.B, st));
         q.done = (unsigned*)t->done.p;
     }
     k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);

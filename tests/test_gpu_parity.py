@@ -374,3 +374,36 @@ def test_fits_table_evaluates_like_arrays(tmp_path, gpu_table, table_arrays):
     q = syn.random_params("kline5", 5, seed=4)
     assert np.array_equal(t2.eval_batch("kline5", q, E), gpu_table.eval_batch("kline5", q, E))
     t2.close()
+
+
+def test_setup_cache_across_calls(gpu_table):
+    """The host pipeline keeps the per-call constants of the last energy grid on the device (k_setup is skipped when the
+    grid, the precision and the model kind repeat): interleaved grids, precisions, model kinds and device-API calls must
+    not change a result."""
+    import torch
+    E1, E2 = syn.energy_grid_linear(300), syn.energy_grid_log(200)
+    p = syn.random_params("kline5", 5, seed=12)
+    pc = syn.random_params("kconv5", 5, seed=13)
+    s2 = syn.powerlaw_continuum(E2)
+    s1 = syn.powerlaw_continuum(E1)
+    ref = {}
+    for key, fn in (("l1", lambda: gpu_table.eval_batch("kline5", p, E1, precision="f32")),
+                    ("l2", lambda: gpu_table.eval_batch("kline5", p, E2, precision="f32")),
+                    ("l1d", lambda: gpu_table.eval_batch("kline5", p, E1, precision="f64")),
+                    ("c2", lambda: gpu_table.eval_batch("kconv5", pc, E2, spectrum=s2, precision="f32")),
+                    ("c1", lambda: gpu_table.eval_batch("kconv5", pc, E1, spectrum=s1, precision="f32"))):
+        gpu_table.eval_batch("kline", syn.CONFIG1_PARAMS, syn.energy_grid_linear(17))   # invalidate with another grid
+        ref[key] = (fn, fn())
+    order = ["l1", "l1", "c1", "c1", "l1", "l1d", "l1d", "l1", "l2", "c2", "c2", "l2", "c1", "l1"]
+    for k in order:
+        fn, want = ref[k]
+        assert np.array_equal(fn(), want, equal_nan=True), k
+    # a device-API call in between overwrites the constants: the next host call must notice
+    dp, dE = torch.from_numpy(p).cuda(), torch.from_numpy(E2).cuda()
+    out = torch.empty((5, 200), dtype=torch.float64, device="cuda")
+    fn, want = ref["l1"]
+    assert np.array_equal(fn(), want)
+    gpu_table.eval_batch_device("kline5", dp, dE, 200, out, 5, precision="f32", stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(fn(), want)
+    assert np.array_equal(out.cpu().numpy(), ref["l2"][1])

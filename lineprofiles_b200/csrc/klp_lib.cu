@@ -228,7 +228,10 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cuda
     const bool fits_one = fixed + fb <= (size_t)t->max_smem_optin;
     const bool fits_want = (size_t)want * (fixed + fb + 1024) <= per_sm;
     const bool global_helps = (size_t)want * (fixed + 1024) <= per_sm;
-    if (fits_one && !t->frame_global && (fits_want || !global_helps)) return launch_quad_impl<T, NT, true>(t, q, fixed + fb, fb, st);
+    // a handful of sets cannot fill the SMs anyway: keep the frame in shared memory, the plan (row bisection, gmin/gmax
+    // lookups) is then not bound by L2 latency
+    const bool tiny = q.B * 4 <= (long long)t->sm_count;
+    if (fits_one && !t->frame_global && (fits_want || !global_helps || tiny)) return launch_quad_impl<T, NT, true>(t, q, fixed + fb, fb, st);
     return launch_quad_impl<T, NT, false>(t, q, fixed, fb, st);
 }
 

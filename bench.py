@@ -281,7 +281,7 @@ def main():
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_spectrum": bytes_per_set, "avg_launch_ms": avg_launch_ms,
                     "sets_per_launch": sets_per_launch,
-                    "note": "the quadrature is FP-issue bound, not HBM bound (SURVEY.md §8d); see roofline_compute"}
+                    "note": "the quadrature is bound by the FP32 datapath of the CUDA cores, not by HBM (SURVEY.md §8d, DESIGN.md §4); see roofline_fp32_pipe, roofline_issue, roofline_compute"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": prec, "data": "synthetic",

@@ -13,6 +13,9 @@ n_bins = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 log = model.startswith("kconv")
 tab = syn.make_table()
 gt = klp.Table.from_arrays(tab, 0)
+for kv in os.environ.get("KLP_OPTIONS", "").split(","):   # e.g. KLP_OPTIONS=conv_mode=1,deposit_ring=1
+    if kv:
+        gt.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 E = syn.energy_grid_log(n_bins) if log else syn.energy_grid_linear(n_bins)
 p = syn.random_params(model, B, seed=1)
 dp, dE = torch.from_numpy(p).cuda(), torch.from_numpy(E).cuda()

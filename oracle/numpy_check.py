@@ -180,3 +180,37 @@ def rebin(flux, g, energy, eline):
             j += 1
         out[i] = s / (0.5 * (energy[i + 1] + energy[i]))
     return out / out.sum()
+
+
+def conv_grid():
+    """convolve_setup (xspec-wrapper.zig:98-105): RangeIterator(f64)(1e-3, 2.0, trunc((2 - 1e-3) / 1e-3) = 1999) (Q16)."""
+    return cumulative_linspace(1e-3, 2.0, 1999)
+
+
+def convolve(g, a, x, b):
+    """convolution.zig:7-102 written as masked array arithmetic: for every source bin i one [n_out, n_window] overlap
+    matrix instead of the reference's scalar scan with `continue` / `break` (g ascending: the bins a scan would skip or
+    stop at are exactly those with bin_high < low, resp. every bin from the first bin_low > high on)."""
+    pos = np.nonzero(a > 0)[0]
+    ws = (pos[0] - 1 if pos[0] > 0 else pos[0]) if pos.size else 0                    # :17-21
+    we = (pos[-1] + 1 if pos[-1] < a.size - 1 else pos[-1]) if pos.size else 0        # :22-29
+    g_min, g_max = g[ws], g[we]
+    bl, bh = g[ws:we], g[ws + 1:we + 1]                                               # window bins [ws, we)
+    bw = bh - bl
+    out = np.zeros(b.size)
+    for i in range(b.size):
+        avg = 2.0 / (x[i + 1] + x[i])
+        low, high = (x[:-1] * avg)[:, None], (x[1:] * avg)[:, None]                  # [n_out, 1]
+        inside = ~((high < g_min) | (low > g_max))                                    # :47
+        BL, BH = bl[None, :], bh[None, :]
+        hit = ~(BH < low)                                                             # not `continue`d ...
+        stop = BL > high                                                              # ... and before the `break`
+        hit &= np.cumsum(stop, axis=1) == 0
+        c2 = (BL < low) & (BH > high)
+        c3 = (BL < low) & (BH < high)
+        c4 = (BL > low) & (BH > high)
+        num = np.where(c2, high - low, np.where(c3, BH - low, np.where(c4, high - BL, 0.0)))
+        overlap = np.where(c2 | c3 | c4, num / bw[None, :], 1.0)                      # Q9: exact coincidences count whole bins
+        weight = np.sum(np.where(hit, a[ws:we][None, :] * bw[None, :] * overlap, 0.0), axis=1)
+        out += np.where(inside[:, 0], weight * b[i], 0.0)
+    return out

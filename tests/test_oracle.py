@@ -233,3 +233,19 @@ def test_numpy_rederivation_agrees_with_oracle(table_arrays, oracle_table):
     ref = oracle_table.eval_batch("kline5", q[None], E, precision="f64", want_fine=True)
     fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5]), E[0], E[-1])
     assert np.max(np.abs(fine - ref["fine"][0])) <= 1e-11 * ref["fine"][0].max()
+
+
+def test_numpy_convolution_agrees_with_oracle(oracle_table):
+    """oracle/numpy_check.convolve (masked array arithmetic, written from convolution.zig) vs the C++ oracle's kconv:
+    the profile on the fixed 1999-point grid (Q16) convolved with a continuum on linear, log and ragged output grids."""
+    from oracle import numpy_check as nc
+    rng = np.random.default_rng(3)
+    grids = [syn.energy_grid_linear(60), syn.energy_grid_log(96), np.sort(rng.uniform(0.2, 9.0, 41))]
+    p = syn.random_params("kconv", 2, seed=21)
+    p[1, 1] = 75.0
+    for E in grids:
+        spec = rng.uniform(0.1, 1.0, E.size - 1)
+        ref = oracle_table.eval_batch("kconv", p, E, spectrum=spec, precision="f64", want_profile=True)
+        for s in range(2):
+            got = nc.convolve(nc.conv_grid(), ref["profile"][s], E, spec)
+            np.testing.assert_allclose(got, ref["out"][s], rtol=1e-11, atol=1e-300)

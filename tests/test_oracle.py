@@ -249,3 +249,18 @@ def test_numpy_convolution_agrees_with_oracle(oracle_table):
         for s in range(2):
             got = nc.convolve(nc.conv_grid(), ref["profile"][s], E, spec)
             np.testing.assert_allclose(got, ref["out"][s], rtol=1e-11, atol=1e-300)
+
+
+def test_numpy_kconv_chain_agrees_with_oracle(table_arrays, oracle_table):
+    """The whole kconv path in numpy (profile on the fixed grid with eline = 1, xspec-wrapper.zig:185-205, then convolve)
+    vs the C++ oracle, f64, one set."""
+    from oracle import numpy_check as nc
+    E = syn.energy_grid_log(64)
+    spec = syn.powerlaw_continuum(E)
+    p = syn.random_params("kconv", 1, seed=5)[0]   # {a, incl, rmin, rmax, alpha}
+    ref = oracle_table.eval_batch("kconv", p[None], E, spectrum=spec, precision="f64", want_profile=True)
+    cg = nc.conv_grid()
+    fine, g = nc.fine_flux(table_arrays, p[0], p[1], 1.0, p[2], p[3], nc.emissivity_fn(p[4]), cg[0], cg[-1])
+    prof = nc.rebin(fine, g, cg, 1.0)
+    np.testing.assert_allclose(prof, ref["profile"][0], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(nc.convolve(cg, prof, E, spec), ref["out"][0], rtol=1e-9, atol=1e-300)

@@ -130,3 +130,13 @@ def test_lmodel_matches_library():
         assert kind == ("con" if name.startswith("kconv") else "add")
     assert [p[0] for p in xm.MODELS["kline5"][1]][:7] == ["a", "incl", "eline", "rmin", "rmax", "rcut", "alpha"]
     assert [p[0] for p in xm.MODELS["kconv"][1]] == ["a", "incl", "rmin", "rmax", "alpha"]
+
+
+def test_committed_ncu_figures_are_what_bench_reads():
+    """profiles/r01_quad_traffic.json (tools/ncu_traffic.py) carries the per-spectrum figures bench.py turns into
+    roofline.traffic, roofline_issue and roofline_fp32_pipe."""
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_quad_traffic.json")))
+    for key in ("sets_per_launch", "dram_bytes_read", "dram_bytes_write", "warp_instructions_per_set", "fma_pipe_cycles_per_set"):
+        assert float(d[key]) > 0, key
+    assert d["sets_per_launch"] == 65535

@@ -264,3 +264,17 @@ def test_numpy_kconv_chain_agrees_with_oracle(table_arrays, oracle_table):
     prof = nc.rebin(fine, g, cg, 1.0)
     np.testing.assert_allclose(prof, ref["profile"][0], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(nc.convolve(cg, prof, E, spec), ref["out"][0], rtol=1e-9, atol=1e-300)
+
+
+def test_numpy_kconv10_chain_agrees_with_oracle(table_arrays, oracle_table):
+    """kconv10 (ten emissivity knots, xspec-wrapper.zig:294-310 parameter layout) through the numpy derivation, f64."""
+    from oracle import numpy_check as nc
+    E = syn.energy_grid_log(48)
+    spec = syn.powerlaw_continuum(E)
+    p = syn.random_params("kconv10", 1, seed=9)[0]   # {a, incl, rmin, rmax, rcut, alpha, e1..e10}
+    ref = oracle_table.eval_batch("kconv10", p[None], E, spectrum=spec, precision="f64", want_profile=True)
+    cg = nc.conv_grid()
+    fine, g = nc.fine_flux(table_arrays, p[0], p[1], 1.0, p[2], p[3], nc.emissivity_fn(p[5], p[6:], p[4]), cg[0], cg[-1])
+    prof = nc.rebin(fine, g, cg, 1.0)
+    np.testing.assert_allclose(prof, ref["profile"][0], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(nc.convolve(cg, prof, E, spec), ref["out"][0], rtol=1e-9, atol=1e-300)

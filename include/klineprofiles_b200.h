@@ -102,7 +102,12 @@ int klp_eval_batch(klp_table* t, int model, int precision, long B, const double*
                    double* out);
 
 /* Same, all pointers are device pointers on the table's device; work is enqueued on
- * `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised. */
+ * `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised.
+ * Concurrency: a table owns one set of device workspaces (fine-grid flux, deposit scratch,
+ * per-call constants), so evaluations on ONE table must not overlap: klp_eval_batch and the XSPEC
+ * symbols serialise themselves (a mutex per table), device-side calls must be ordered by the
+ * caller (same stream, or events between streams).  Concurrent walkers use one table per stream --
+ * the frames are shared read-only data, a second table costs a second copy of them. */
 int klp_eval_batch_device(klp_table* t, int model, int precision, long B, const double* d_params,
                           const double* d_energy, int n_flux, const double* d_spectrum,
                           int spectrum_per_set, double* d_out, void* cuda_stream);

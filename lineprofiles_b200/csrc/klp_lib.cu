@@ -998,7 +998,6 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "conv_mode") {
         if (value < 0 || value > 1) return fail(KLP_ERR_ARG, "conv_mode");
         t->conv_mode = (int)value;
-
     } else if (k == "fast") {
         t->use_fast = value != 0;
     } else if (k == "chunk") {

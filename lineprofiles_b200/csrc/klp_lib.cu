@@ -9,6 +9,8 @@
 #include "../../include/klineprofiles_b200.h"
 #include "klp_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -88,6 +90,13 @@ struct PinBuf {
         return KLP_OK;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Profiler ranges where the reference has its Tracy zone (InterpolatingTransferFunction.integrate,
+// transfer-functions.zig:141-142): one range per host call and one per launch group.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 struct EvalExtra {
@@ -329,6 +338,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             q.order = (const int*)t->order.p;
         }
         {
+            NvtxRange nvtx_quad("klp integrate (k_quad)");
             TimedLaunch tl(t, st, 1);
             if ((rc = launch_quad<T>(t, q, st))) return rc;
         }
@@ -434,6 +444,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     for (int i = 0; i < n_flux; ++i)
         if (!(energy[i + 1] > energy[i])) return fail(KLP_ERR_ARG, "energy edges must be strictly ascending");
     std::lock_guard<std::mutex> lk(t->mu_);
+    NvtxRange nvtx_call("klp_eval_batch");
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     int rc;

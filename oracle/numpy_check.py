@@ -1,4 +1,8 @@
-"""Independent numpy (f64) re-derivation of the kline / kline5 fine-grid flux.  TEST INFRASTRUCTURE ONLY.
+"""Independent numpy re-derivation of the kline / kline5 fine-grid flux, the rebin and the convolution.  TEST
+INFRASTRUCTURE ONLY.  Every function takes the element type: np.float64 (the gate mode) or np.float32 -- the reference's own
+type (xspec-wrapper.zig:61), where numpy's element-wise IEEE arithmetic reproduces the reference's roundings operation by
+operation, so that the comparison with the C++ oracle in its faithful f32 mode is BIT FOR BIT (cos / pow / log10 are
+evaluated in f64 and rounded, the oracle's stated policy).
 
 Written from the reference source (file:line cited below), not from oracle/klp_oracle.cpp, and
 structured differently on purpose: vectorised over the 1999 fine bins per radius with masks instead
@@ -18,10 +22,29 @@ GW = np.array([1.2948496616886969327061143267787e-01, 2.797053914892766679014677
                3.8183005050511894495036977548818e-01, 4.1795918367346938775510204081658e-01])
 
 
-def cumulative_linspace(lo, hi, n):
-    """RangeIterator (utils.zig:121-156): current += delta."""
-    delta = (hi - lo) / float(n - 1)
-    return np.cumsum(np.concatenate([[lo], np.full(n - 1, delta)]))   # cumsum is a sequential sum
+import math as _math
+
+# Transcendentals: the same policy as the C++ oracle and the CUDA path (oracle/klp_oracle.cpp header): evaluated in f64 by
+# the C library and rounded to the element type (Zig's own f32 implementations cannot be run here).
+
+
+def _pow(F, x, y):
+    return F(_math.pow(float(x), float(y)))
+
+
+def _cos(F, x):
+    return F(_math.cos(float(x)))
+
+
+def _log10(F, x):
+    return F(_math.log10(float(x)))
+
+
+def cumulative_linspace(lo, hi, n, F=np.float64):
+    """RangeIterator (utils.zig:121-156): current += delta, in the element type."""
+    lo, hi = F(lo), F(hi)
+    delta = (hi - lo) / F(n - 1)
+    return np.cumsum(np.concatenate([[lo], np.full(n - 1, delta, F)]).astype(F), dtype=F)   # a sequential sum in F
 
 
 def first_geq(arr, v):
@@ -29,15 +52,16 @@ def first_geq(arr, v):
     return int(idx[0]) if idx.size else None
 
 
-def blend(tab, a, mu):
+def blend(tab, a, mu, F=np.float64):
     """line-profile.zig:116-231 (Q5, Q14, Q15)."""
-    spins, mus, n_mu = tab["spins"].astype(np.float64), tab["mus"].astype(np.float64), tab["n_mu"]
+    spins, mus, n_mu = tab["spins"].astype(F), tab["mus"].astype(F), tab["n_mu"]
+    a, mu = F(a), F(mu)
     i0 = first_geq(spins, a) or 0
     i1 = first_geq(mus, mu) or 0
 
     def frame(ia, im):
         f = ia * n_mu + im
-        return {k: tab[k][f].astype(np.float64) for k in ("radii", "gmin", "gmax", "upper", "lower")}
+        return {k: tab[k][f].astype(F) for k in ("radii", "gmin", "gmax", "upper", "lower")}
 
     def lerp(A, B, w):   # (y1 - y0) * w + y0, utils.zig:43-51
         return {k: (B[k] - A[k]) * w + A[k] for k in A}
@@ -54,39 +78,43 @@ def blend(tab, a, mu):
     return c1
 
 
-def emissivity_fn(alpha, knots=None, rcut=None):
-    """emissivity.zig:4-78 with init(weights, 1.0, rcut, alpha) (Q8)."""
+def emissivity_fn(alpha, knots=None, rcut=None, F=np.float64):
+    """emissivity.zig:4-78 with init(weights, 1.0, rcut, alpha) (Q8); the power law is constructed with -alpha
+    (xspec-wrapper.zig:352,401)."""
+    alpha = F(alpha)
     if knots is None:
-        return lambda r: r ** (-alpha)
+        return lambda r: _pow(F, r, -alpha)
+    knots = np.asarray(knots).astype(F)
     n = len(knots)
-    logr = cumulative_linspace(np.log10(1.0), np.log10(rcut), n + 1)[1:]
-    logc = np.empty(n)
+    logr = cumulative_linspace(_log10(F, 1.0), _log10(F, F(rcut)), n + 1, F)[1:]
+    logc = np.empty(n, F)
     logc[n - 1] = logr[n - 1] * (knots[n - 1] - alpha)
     for i in range(n - 2, -1, -1):
         logc[i] = logc[i + 1] + logr[i] * (knots[i] - knots[i + 1])
-    radii, coeffs = 10.0 ** logr, 10.0 ** logc
+    radii = np.array([_pow(F, 10.0, v) for v in logr], F)
+    coeffs = np.array([_pow(F, 10.0, v) for v in logc], F)
 
     def eps(r):
         i = first_geq(radii, r)
-        return r ** (-alpha) if i is None else coeffs[i] * r ** (-knots[i])
+        return _pow(F, r, -alpha) if i is None else coeffs[i] * _pow(F, r, -knots[i])
     return eps
 
 
-def fine_flux(tab, a, incl_deg, eline, rmin, rmax, eps, e_first, e_last, lim=(None, None)):
-    """flux_cache after itf.integrate (xspec-wrapper.zig:147-160, transfer-functions.zig:274-384), f64."""
+def fine_flux(tab, a, incl_deg, eline, rmin, rmax, eps, e_first, e_last, lim=(None, None), F=np.float64):
+    """flux_cache after itf.integrate (xspec-wrapper.zig:147-160, transfer-functions.zig:274-384) in the element type F."""
     n_g = tab["n_g"]
-    mu = np.cos(incl_deg * 0.017453292519943295769236907684886127)
-    fr = blend(tab, a, mu)
-    gs = cumulative_linspace(H, 1.0 - H, n_g)                           # utils.zig:219-232
-    g = cumulative_linspace(e_first, e_last, N_FINE) * (1.0 / eline)    # refine_grid :117-132
+    mu = _cos(F, F(incl_deg) * 0.017453292519943295769236907684886127)
+    fr = blend(tab, a, mu, F)
+    gs = cumulative_linspace(H, 1.0 - H, n_g, F)                        # utils.zig:219-232
+    g = cumulative_linspace(e_first, e_last, N_FINE, F) * (F(1) / F(eline))    # refine_grid :117-132
     # radial grid :149-153 with the fresh setup() limits (:84)
-    base = 1.0 / cumulative_linspace(1.0 / 50.0, 1.0 / 1.0, N_RAD)[::-1]
-    lo = max(base[0] if lim[0] is None else lim[0], rmin)
-    hi = min(rmax, base[-1] if lim[1] is None else lim[1])
-    r_grid = (1.0 / cumulative_linspace(1.0 / hi, 1.0 / lo, N_RAD))[::-1]
+    base = (F(1) / cumulative_linspace(F(1) / F(50), F(1) / F(1), N_RAD, F))[::-1]
+    lo = max(base[0] if lim[0] is None else F(lim[0]), F(rmin))
+    hi = min(F(rmax), base[-1] if lim[1] is None else F(lim[1]))
+    r_grid = (F(1) / cumulative_linspace(F(1) / hi, F(1) / lo, N_RAD, F))[::-1]
     radii = fr["radii"]
-    flux = np.zeros(N_FINE - 1)
-    gmin = gmax = 0.0
+    flux = np.zeros(N_FINE - 1, F)
+    gmin = gmax = F(0)
     sqrtH = 0.022360679774997896964091736687313
 
     def integrand(x, cl, cu, gmin, gmax):
@@ -126,20 +154,22 @@ def fine_flux(tab, a, incl_deg, eline, rmin, rmax, eps, e_first, e_last, lim=(No
             continue
         gl, gh = glow[act].copy(), ghigh[act].copy()
         dg = gmax - gmin
-        sl, sh = (gl - gmin) / dg, (gh - gmin) / dg
-        val = np.zeros(act.size)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sl, sh = (gl - gmin) / dg, (gh - gmin) / dg
+        val = np.zeros(act.size, F)
         gauss = np.ones(act.size, bool)
 
         def edge(lim, lim_star):                                  # Q17
             k = dg * lim_star + gmin
-            return 2 * np.abs(np.sqrt(k) - np.sqrt(lim)) * integrand(k, cl, cu, gmin, gmax) * sqrtH * dg
+            with np.errstate(invalid="ignore"):
+                return 2 * np.abs(np.sqrt(k) - np.sqrt(lim)) * integrand(k, cl, cu, gmin, gmax) * sqrtH * dg
 
         lo_edge = sl < H
         both = lo_edge & (sh > H)
         only = lo_edge & ~(sh > H)
         if both.any():
-            val[both] += edge(gl[both], np.full(both.sum(), H))
-            gl[both] = dg * H + gmin
+            val[both] += edge(gl[both], np.full(both.sum(), H, F))
+            gl[both] = dg * F(H) + gmin
         if only.any():
             val[only] += edge(gl[only], sh[only])
             gauss[only] = False
@@ -147,20 +177,20 @@ def fine_flux(tab, a, incl_deg, eline, rmin, rmax, eps, e_first, e_last, lim=(No
         both = hi_edge & (sl < 1 - H)
         only = hi_edge & ~(sl < 1 - H)
         if both.any():
-            val[both] += edge(gh[both], np.full(both.sum(), 1 - H))
-            gh[both] = dg * (1 - H) + gmin
+            val[both] += edge(gh[both], np.full(both.sum(), 1 - H, F))
+            gh[both] = dg * F(1 - H) + gmin
         if only.any():
             val[only] += edge(gh[only], sl[only])
             gauss[only] = False
         if gauss.any():
             a_, b_ = gl[gauss], gh[gauss]
             scale = (b_ - a_) / 2
-            s = np.zeros(a_.size)
+            s = np.zeros(a_.size, F)
             for k in range(3):
-                xp = (GX[k] + 1.0) * scale + a_
-                xm = (-GX[k] + 1.0) * scale + a_
-                s = s + (integrand(xp, cl, cu, gmin, gmax) + integrand(xm, cl, cu, gmin, gmax)) * (GW[k] * scale)
-            s = s + integrand(scale + a_, cl, cu, gmin, gmax) * GW[3]     # Q1
+                xp = (float(GX[k]) + 1.0) * scale + a_            # (xi + 1) is a comptime constant, Integrator.zig:50-51
+                xm = (-float(GX[k]) + 1.0) * scale + a_
+                s = s + (integrand(xp, cl, cu, gmin, gmax) + integrand(xm, cl, cu, gmin, gmax)) * (float(GW[k]) * scale)
+            s = s + integrand(scale + a_, cl, cu, gmin, gmax) * float(GW[3])     # Q1
             val[gauss] += s
         val = val * weight
         val[~np.isfinite(val)] = 0                                # Q12
@@ -168,18 +198,22 @@ def fine_flux(tab, a, incl_deg, eline, rmin, rmax, eps, e_first, e_last, lim=(No
     return flux, g
 
 
-def rebin(flux, g, energy, eline):
-    """xspec-wrapper.zig:162-182 (Q3, Q10)."""
-    inorm = 1.0 / eline
+def rebin(flux, g, energy, eline, F=np.float64):
+    """xspec-wrapper.zig:162-182 (Q3, Q10): partial sums in F, the comparison and everything after in f64, with the
+    reciprocal of eline rounded to F first."""
+    inorm = float(F(1) / F(eline))
     out = np.zeros(energy.size - 1)
     j = 0
     for i in range(out.size):
-        s = 0.0
-        while j < flux.size and g[j] < energy[i] * inorm:
-            s += flux[j]
+        s = F(0)
+        while j < flux.size and float(g[j]) < energy[i] * inorm:
+            s = s + flux[j]
             j += 1
-        out[i] = s / (0.5 * (energy[i + 1] + energy[i]))
-    return out / out.sum()
+        out[i] = float(s) / (0.5 * (energy[i + 1] + energy[i]))
+    total = 0.0
+    for v in out:                      # total_flux += flux[i], sequentially
+        total += float(v)
+    return out / total
 
 
 def conv_grid():
@@ -211,6 +245,7 @@ def convolve(g, a, x, b):
         c4 = (BL > low) & (BH > high)
         num = np.where(c2, high - low, np.where(c3, BH - low, np.where(c4, high - BL, 0.0)))
         overlap = np.where(c2 | c3 | c4, num / bw[None, :], 1.0)                      # Q9: exact coincidences count whole bins
-        weight = np.sum(np.where(hit, a[ws:we][None, :] * bw[None, :] * overlap, 0.0), axis=1)
+        terms = np.where(hit, a[ws:we][None, :] * bw[None, :] * overlap, 0.0)
+        weight = np.cumsum(terms, axis=1)[:, -1] if terms.shape[1] else np.zeros(x.size - 1)   # sequential, as `weight +=`
         out += np.where(inside[:, 0], weight * b[i], 0.0)
     return out

@@ -278,3 +278,34 @@ def test_numpy_kconv10_chain_agrees_with_oracle(table_arrays, oracle_table):
     prof = nc.rebin(fine, g, cg, 1.0)
     np.testing.assert_allclose(prof, ref["profile"][0], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(nc.convolve(cg, prof, E, spec), ref["out"][0], rtol=1e-9, atol=1e-300)
+
+
+def test_numpy_f32_restatement_is_bit_identical_to_oracle(table_arrays, oracle_table):
+    """The reference's own element type: numpy float32 arithmetic (element-wise IEEE, no contraction) reproduces the
+    reference's roundings operation by operation, so the independently written, vectorised restatement and the C++ oracle
+    in faithful f32 mode must agree BIT FOR BIT -- fine-grid flux and output spectrum, kline / kline5 / kconv."""
+    from oracle import numpy_check as nc
+    F = np.float32
+    E = syn.energy_grid_linear(1000)
+    p = syn.CONFIG1_PARAMS[0]
+    ref = oracle_table.eval_batch("kline", p[None], E, precision="f32", want_fine=True)
+    fine, g = nc.fine_flux(table_arrays, p[0], p[1], p[2], p[3], p[4], nc.emissivity_fn(p[5], F=F), E[0], E[-1], F=F)
+    assert np.array_equal(fine.astype(np.float64), ref["fine"][0])
+    assert np.array_equal(nc.rebin(fine, g, E, p[2], F=F), ref["out"][0])
+    P = syn.random_params("kline5", 3, seed=77)
+    P[0, 1], P[1, 1] = 72.0, 84.9
+    ref = oracle_table.eval_batch("kline5", P, E, precision="f32", want_fine=True)
+    for s, q in enumerate(P):
+        fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5], F=F), E[0], E[-1], F=F)
+        assert np.array_equal(fine.astype(np.float64), ref["fine"][s])
+        assert np.array_equal(nc.rebin(fine, g, E, q[2], F=F), ref["out"][s])
+    # kconv: f32 profile on the fixed f64 grid (refine_grid casts its end points to f32, xspec-wrapper.zig:125), f64 convolution
+    El = syn.energy_grid_log(64)
+    spec = syn.powerlaw_continuum(El)
+    k = syn.random_params("kconv", 1, seed=5)[0]
+    ref = oracle_table.eval_batch("kconv", k[None], El, spectrum=spec, precision="f32", want_profile=True)
+    cg = nc.conv_grid()
+    fine, g = nc.fine_flux(table_arrays, k[0], k[1], 1.0, k[2], k[3], nc.emissivity_fn(k[4], F=F), cg[0], cg[-1], F=F)
+    prof = nc.rebin(fine, g, cg, 1.0, F=F)
+    assert np.array_equal(prof, ref["profile"][0])
+    assert np.array_equal(nc.convolve(cg, prof, El, spec), ref["out"][0])

@@ -309,3 +309,14 @@ def test_numpy_f32_restatement_is_bit_identical_to_oracle(table_arrays, oracle_t
     prof = nc.rebin(fine, g, cg, 1.0, F=F)
     assert np.array_equal(prof, ref["profile"][0])
     assert np.array_equal(nc.convolve(cg, prof, El, spec), ref["out"][0])
+
+
+def test_numpy_golden_equals_oracle_golden():
+    """tests/golden/numpy_golden.npz (f32 spectra of all five models from the numpy restatement,
+    tests/golden/make_numpy_golden.py) and oracle_golden.npz (from the C++ oracle) are bit-identical: the vectors the CUDA
+    path is checked against on the GPU box have been produced twice, by two separately written implementations."""
+    a = np.load(os.path.join(os.path.dirname(GOLD), "numpy_golden.npz"))
+    b = np.load(GOLD)
+    assert sorted(a.files) == sorted(f"out_{m}_f32" for m in ("kline", "kline5", "kconv", "kconv5", "kconv10"))
+    for k in a.files:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k

@@ -320,3 +320,34 @@ def test_numpy_golden_equals_oracle_golden():
     assert sorted(a.files) == sorted(f"out_{m}_f32" for m in ("kline", "kline5", "kconv", "kconv5", "kconv10"))
     for k in a.files:
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def _same_bits(a, b):
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def test_numpy_f32_restatement_on_edge_and_irregular_sets(table_arrays, oracle_table):
+    """The parameter sets of the GPU edge tests (out-of-table spin / inclination, rmin > rmax, zero knots, rcut = 1, eline
+    negative / NaN / huge / tiny / inf) through the numpy f32 restatement: bit-identical to the oracle, NaNs included."""
+    import warnings
+    from oracle import numpy_check as nc
+    F = np.float32
+    E = syn.energy_grid_linear(300)
+    p = syn.random_params("kline5", 14, seed=31)
+    p[0, 0] = 1.7
+    p[1, 0] = -0.9
+    p[2, 1] = 0.0
+    p[3, 1] = 90.0
+    p[4, 3:5] = (30.0, 10.0)
+    p[5, 7:] = 0.0
+    p[6, 5] = 1.0
+    p[7, 3:5] = (1.0, 1000.0)
+    p[8, 6] = 10.0
+    p[9:14, 2] = (-6.4, np.nan, 1e6, 1e-3, 0.5)
+    ref = oracle_table.eval_batch("kline5", p, E, precision="f32", want_fine=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for s, q in enumerate(p):
+            fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5], F=F), E[0], E[-1], F=F)
+            assert _same_bits(fine.astype(np.float64), ref["fine"][s]), s
+            assert _same_bits(nc.rebin(fine, g, E, q[2], F=F), ref["out"][s]), s

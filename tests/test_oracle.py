@@ -351,3 +351,19 @@ def test_numpy_f32_restatement_on_edge_and_irregular_sets(table_arrays, oracle_t
             fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5], F=F), E[0], E[-1], F=F)
             assert _same_bits(fine.astype(np.float64), ref["fine"][s]), s
             assert _same_bits(nc.rebin(fine, g, E, q[2], F=F), ref["out"][s]), s
+
+
+def test_numpy_f32_restatement_follows_the_ratchet(table_arrays, oracle_table):
+    """Q2 through the numpy restatement: the second call of a process starts from the radial limits the first one left
+    (set_radial_grid reads the CURRENT r_grid, xspec-wrapper.zig:149-153) -- bit-identical to the oracle's ratchet mode."""
+    from oracle import numpy_check as nc
+    F = np.float32
+    E = syn.energy_grid_linear(100)
+    p = np.array([[0.5, 40, 6.4, 5.0, 20.0, 3.0], [0.5, 40, 6.4, 1.0, 400.0, 3.0]])
+    lo, hi = orc.base_limits("f32")
+    first = oracle_table.eval_batch("kline", p[:1], E, precision="f32", ratchet=True, lims=[lo, hi])
+    both = oracle_table.eval_batch("kline", p, E, precision="f32", ratchet=True, lims=[lo, hi])
+    q = p[1]
+    fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[5], F=F), E[0], E[-1],
+                           lim=tuple(first["lims"]), F=F)
+    assert np.array_equal(nc.rebin(fine, g, E, q[2], F=F), both["out"][1])

@@ -140,3 +140,33 @@ def test_committed_ncu_figures_are_what_bench_reads():
     for key in ("sets_per_launch", "dram_bytes_read", "dram_bytes_write", "warp_instructions_per_set", "fma_pipe_cycles_per_set"):
         assert float(d[key]) > 0, key
     assert d["sets_per_launch"] == 65535
+
+
+def test_c99_client_links_and_gets_the_xspec_error_convention(tmp_path):
+    """A plain C99 translation unit (what XSPEC's initpackage glue is) includes the header with -pedantic, links the
+    library and calls `kline` without a table: message with the reference's prefix on stderr, flux zero-filled
+    (xspec-wrapper.zig:361-372)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include "klineprofiles_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "    double e[3] = {1.0, 2.0, 3.0}, p[6] = {0.5, 30, 6.4, 1.0, 400.0, 3.0}, f[2] = {7, 7};\n"
+        '    printf("%d %d\\n", klp_model_nparams(KLP_KLINE), klp_model_nparams(KLP_KCONV10));\n'
+        '    kline(e, 2, p, 0, f, 0, "");\n'
+        '    printf("%g %g\\n", f[0], f[1]);\n'
+        "    return 0;\n}\n")
+    libdir = os.path.dirname(klp.api.library_path())
+    exe = tmp_path / "client"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                         "-o", str(exe), "-L", libdir, "-lklineprofiles_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    env = dict(os.environ, KLINE_PROF_DATA_DIR=str(tmp_path / "nowhere"))
+    run = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert run.returncode == 0
+    assert run.stdout.split() == ["6", "16", "0", "0"]
+    assert "kerrlineprofile: " in run.stderr and "MODEL OUTPUT SET TO ZERO" in run.stderr

@@ -133,7 +133,7 @@ int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d
 int klp_set_timing(klp_table* t, int enable);
 int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 
-/* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default), "splits" (CTAs
+/* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default: 1024 in f32, 512 in f64), "splits" (CTAs
  * that share one set, 0 = auto: more than one only when the batch is smaller than the GPU), "conv_mode" (0 = the
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
  * faster, equal to rounding), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring and add them

@@ -246,7 +246,9 @@ template <class T, int NT> int launch_quad_nt(klp_table* t, QuadArgs<T>& q, cuda
 
 template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st) {
     int nt = t->quad_threads;
-    if (nt <= 0) nt = 512;
+    // measured (tools/nt_probe.py): f32 -- one 1024-thread CTA per SM beats two of 512 at every batch size (+1.5 % at 5e4
+    // sets, +6 % at 2000: one plan per SM instead of two, 32 warps either way); f64 -- 1024 threads spill, 512 it is
+    if (nt <= 0) nt = sizeof(T) == 4 ? 1024 : 512;
     switch (nt) {
         case 256: return launch_quad_nt<T, 256>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);

@@ -10,8 +10,8 @@
 // The only known answers it holds are the index identities of main.zig:19-30 and the
 // RangeIterator identities of utils.zig:158-171; those are pinned in tests/.  For flux values:
 // **parity unpinned** -- this restatement is the authority, cross-checked by an independently
-// written numpy restatement (oracle/numpy_check.py: bit-identical to this file's f32 mode on fine
-// flux, spectra, conv profile and convolved spectrum; 1e-11 in f64 mode) and by property tests.
+// written numpy restatement (oracle/numpy_check.py: bit-identical to this file in both modes on
+// fine flux, spectra, conv profile and convolved spectrum) and by property tests.
 //
 // Precision modes (template parameter T):
 //   T = float   "faithful": every operation in the type the reference instantiates

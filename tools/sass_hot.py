@@ -1,7 +1,7 @@
 """Static size of the k_quad hot loops of a library build: usage sass_hot.py LIB [function-substring]"""
 import re, subprocess, sys, collections
 lib = sys.argv[1]
-want = sys.argv[2] if len(sys.argv) > 2 else "k_quadIfLi512ELb0"
+want = sys.argv[2] if len(sys.argv) > 2 else "k_quadIfLi1024ELb1"   # the default f32 configuration
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 cur = None; fns = {}
 for l in txt.splitlines():

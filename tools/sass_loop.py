@@ -1,12 +1,13 @@
-"""Print head/tail of the first hot loop (>= 90 packed instr) of k_quad<float,512,false>: sass_loop.py LIB [nhead] [ntail]"""
+"""Print head/tail of the first hot loop (>= 90 packed instr) of k_quad<float,1024,frame in smem>: sass_loop.py LIB [nhead] [ntail] [function-substring]"""
 import re, subprocess, sys
 lib = sys.argv[1]; nh = int(sys.argv[2]) if len(sys.argv) > 2 else 36; nt = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+want = sys.argv[4] if len(sys.argv) > 4 else "k_quadIfLi1024ELb1"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 cur = None; ins = []
 for l in txt.splitlines():
     m = re.search(r"Function : (\S+)", l)
     if m: cur = m.group(1); continue
-    if cur and "k_quadIfLi512ELb0" in cur:
+    if cur and want in cur:
         m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
         if m: ins.append((int(m.group(1), 16), m.group(2)))
 for a, t in ins:

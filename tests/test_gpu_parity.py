@@ -161,7 +161,7 @@ def test_irregular_fine_grids(gpu_table, oracle_table):
     # the options that move the blended frame / change the CTA shape must not change a bit
     base = gpu_table.eval_batch("kline5", p, E, precision="f32")
     try:
-        for key, val in (("frame_global", 1), ("quad_threads", 256), ("quad_threads", 1024), ("deposit_ring", 1)):
+        for key, val in (("frame_global", 1), ("quad_threads", 256), ("quad_threads", 512), ("quad_threads", 1024), ("deposit_ring", 1)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base, equal_nan=True), (key, val)
             gpu_table.set_option(key, 0)
@@ -214,7 +214,7 @@ def test_invariance_to_batching_knobs(gpu_table):
     perm = np.random.default_rng(0).permutation(700)
     assert np.array_equal(gpu_table.eval_batch("kline5", p[perm], E, precision="f32"), base[perm])
     try:
-        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1), ("deposit_ring", 1), ("order", 0)):
+        for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 512), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1), ("deposit_ring", 1), ("order", 0)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
             gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0, "order": 1}[key])

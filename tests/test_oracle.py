@@ -366,3 +366,16 @@ def test_numpy_f32_restatement_follows_the_ratchet(table_arrays, oracle_table):
     fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[5], F=F), E[0], E[-1],
                            lim=tuple(first["lims"]), F=F)
     assert np.array_equal(nc.rebin(fine, g, E, q[2], F=F), both["out"][1])
+
+
+@pytest.mark.parametrize("n_bins", [1, 7, 2500])
+def test_numpy_f32_restatement_on_ragged_grids(table_arrays, oracle_table, n_bins):
+    """One-bin, short and finer-than-the-fine-grid ragged output grids (the rebin walks its index past empty output bins,
+    xspec-wrapper.zig:162-182): bit-identical to the oracle."""
+    from oracle import numpy_check as nc
+    F = np.float32
+    E = np.sort(np.random.default_rng(n_bins).uniform(0.3, 9.5, n_bins + 1))
+    q = syn.random_params("kline5", 1, seed=9)[0]
+    ref = oracle_table.eval_batch("kline5", q[None], E, precision="f32")["out"][0]
+    fine, g = nc.fine_flux(table_arrays, q[0], q[1], q[2], q[3], q[4], nc.emissivity_fn(q[6], q[7:], q[5], F=F), E[0], E[-1], F=F)
+    assert _same_bits(nc.rebin(fine, g, E, q[2], F=F), ref)

@@ -4,7 +4,8 @@
  * reference exports (`pub export fn ... callconv(.c)`, reference src/xspec-wrapper.zig:425-530)
  * and that xspec/lmodel.dat:1,9,23,30,43 binds as c_kline ... c_kconv10.  Everything prefixed
  * klp_ is new: the reference evaluates one parameter set per call on one CPU thread; this
- * library evaluates batches of independent parameter sets on one B200 per process.
+ * library evaluates batches of independent parameter sets on one B200 per table, and on all
+ * the B200s of a box through a klp_group.
  *
  * There is NO CPU fallback: every evaluation entry point returns KLP_ERR_CUDA (or, for the
  * XSPEC symbols, logs and zero-fills like the reference does on error) when no CUDA device is
@@ -41,8 +42,10 @@ enum {
     KLP_OK = 0,
     KLP_ERR_ARG = 1,      /* bad argument */
     KLP_ERR_CUDA = 2,     /* CUDA runtime failure / no device */
-    KLP_ERR_IO = 3,       /* table file missing or malformed */
-    KLP_ERR_NOMEM = 4
+    KLP_ERR_IO = 3,       /* table file malformed (truncated, unsupported TFORM, HDU/frame-count mismatch ...) */
+    KLP_ERR_NOMEM = 4,
+    KLP_ERR_NOTFOUND = 5, /* table file cannot be opened (the XSPEC symbols then print the reference's KLINE_PROF_DATA_DIR hint) */
+    KLP_ERR_NCCL = 6      /* NCCL not loadable or a collective failed (multi-GPU entry points only) */
 };
 
 typedef struct klp_table klp_table; /* host + device copy of a transfer-function table, plus workspaces */
@@ -127,9 +130,10 @@ int klp_eval_debug(klp_table* t, int model, int precision, long B, const double*
 int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d_a_incl, void* d_out,
                             void* cuda_stream);
 
-/* Per-kernel device time of the most recent klp_eval_batch_device call when timing is enabled
- * (klp_set_timing(t, 1)): ms[0] setup, ms[1] quadrature, ms[2] rebin, ms[3] convolution;
- * launches[4] likewise.  Enabling timing adds cudaEvent records on the caller's stream. */
+/* Per-kernel device time accumulated over every evaluation of this table since timing was enabled
+ * (klp_set_timing(t, 1)) or last read: ms[0] setup, ms[1] quadrature, ms[2] rebin, ms[3] convolution;
+ * launches[4] likewise.  Reading resets the accumulation.  Enabling timing adds cudaEvent records on
+ * the stream the kernels are launched on. */
 int klp_set_timing(klp_table* t, int enable);
 int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 
@@ -143,6 +147,12 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);
 
+/* What the most recent quadrature launch of this table was: "k_quad<float, 1024, 1> splits=1 ring=0 fast_frames=600/600"
+ * (template instantiation = element type, CTA threads, blended frame in shared memory; CTAs per set; deposit-ring mode; how
+ * many table frames pass the operand-range check of the branch-free arithmetic).  bench.py compares it with the kernel name
+ * of the committed ncu capture before quoting per-instruction figures from that capture. */
+int klp_last_launch_info(klp_table* t, char* buf, size_t len);
+
 /* Self-test of the branch-free exact-arithmetic sequences (klp_kernels.cuh: div_by, div_gen, sqrt_gen)
  * against the IEEE intrinsics on n_total random + adversarial operands drawn from the ranges they are
  * licensed for.  mismatches4: f32 div_by, f64 div_by, f32 div_gen, f32 sqrt_gen -- all must be 0. */
@@ -152,6 +162,46 @@ int klp_arith_selftest(klp_table* t, unsigned long long seed, unsigned long long
 /* Peak-rate microbenchmark on the table's device: dependent-chain-free FMA throughput in
  * GFLOP/s for precision f32 / f64 (denominator of the compute roofline). */
 int klp_fma_peak_gflops(klp_table* t, int precision, double* gflops);
+
+/* ---- several GPUs behind the C ABI (BASELINE.json north_star) -----------------
+ * The reference is a single-process, single-thread library (xspec-wrapper.zig:425-530 are plain C calls;
+ * XSPEC `parallel` forks).  Independent parameter sets are sharded over the GPUs of one box -- every
+ * lookup of the reference is pure (Q18), there is no cross-set exchange -- each GPU holding a replica of
+ * the table.  A group is formed either by ONE process that drives n GPUs (klp_group_create_local: what a
+ * Zig / XSPEC / Julia host needs) or by one process per GPU (klp_group_create_rank: torchrun / mpirun; the
+ * 128-byte id comes from klp_nccl_unique_id on one rank and is distributed by the host).  NCCL is loaded
+ * with dlopen at first use; without it everything except the device-resident gather still works.
+ * A group borrows its tables: destroy the group first. */
+typedef struct klp_group klp_group;
+int klp_nccl_unique_id(void* id128);
+int klp_nccl_version(int* version);
+int klp_group_create_local(klp_table* const* tables, int n, klp_group** out);
+int klp_group_create_rank(klp_table* table, const void* id128, int rank, int nranks, klp_group** out);
+void klp_group_destroy(klp_group* g);
+int klp_group_size(const klp_group* g, int* n_local, int* nranks);
+
+/* Host buffers, local groups: klp_eval_batch over all GPUs of the group.  Contiguous blocks of
+ * ceil(B / n) sets per GPU, one host thread and one pinned double-buffered pipeline per GPU, every GPU
+ * copies its spectra straight into its slice of `out` -- no collective is needed. */
+int klp_group_eval_batch(klp_group* g, int model, int precision, long B, const double* params,
+                         const double* energy, int n_flux, const double* spectrum, int spectrum_per_set,
+                         double* out);
+
+/* Device-resident buffers: member i (i < n_local) evaluates the B_local sets of d_params[i] -- rank r of
+ * the group owns the global sets [r * B_local, (r+1) * B_local) -- and EVERY member ends up with all
+ * nranks * B_local spectra in d_out_all[i], laid out [rank][set][bin].  The batch is processed in chunks
+ * (option "gather_chunk", default 16384 sets): while chunk k+1 is integrated, the spectra of chunk k
+ * travel over NVLink on a second, high-priority stream -- one grouped NCCL operation per chunk (a single
+ * ncclAllGather when the batch is one chunk).  Arrays have n_local entries; d_spectrum may be NULL for
+ * kline / kline5; cuda_streams may be NULL (the group's own streams; see klp_group_synchronize).
+ * Asynchronous: d_out_all[i] is complete in stream order on cuda_streams[i]. */
+int klp_group_eval_allgather_device(klp_group* g, int model, int precision, long B_local,
+                                    const double* const* d_params, const double* const* d_energy, int n_flux,
+                                    const double* const* d_spectrum, int spectrum_per_set,
+                                    double* const* d_out_all, void* const* cuda_streams);
+int klp_group_synchronize(klp_group* g);
+int klp_group_set_option(klp_group* g, const char* key, long value);
+int klp_group_last_gather_ops(const klp_group* g);   /* NCCL group operations issued by the last device-resident call */
 
 /* ---- the XSPEC model surface (reference xspec-wrapper.zig:425-530) -------------------------
  * void f(const double* energy   n_flux+1 bin edges,

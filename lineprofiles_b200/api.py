@@ -64,8 +64,22 @@ def load_library():
     L.klp_set_timing.argtypes = [vp, C.c_int]
     L.klp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_long)]
     L.klp_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.klp_last_launch_info.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.klp_fma_peak_gflops.argtypes = [vp, C.c_int, dp]
     L.klp_arith_selftest.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    pvp = C.POINTER(vp)
+    L.klp_nccl_unique_id.argtypes = [C.c_char_p]
+    L.klp_nccl_version.argtypes = [C.POINTER(C.c_int)]
+    L.klp_group_create_local.argtypes = [pvp, C.c_int, pvp]
+    L.klp_group_create_rank.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, pvp]
+    L.klp_group_destroy.argtypes = [vp]
+    L.klp_group_destroy.restype = None
+    L.klp_group_size.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.klp_group_eval_batch.argtypes = [vp, C.c_int, C.c_int, C.c_long, dp, dp, C.c_int, dp, C.c_int, dp]
+    L.klp_group_eval_allgather_device.argtypes = [vp, C.c_int, C.c_int, C.c_long, pvp, pvp, C.c_int, pvp, C.c_int, pvp, pvp]
+    L.klp_group_synchronize.argtypes = [vp]
+    L.klp_group_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.klp_group_last_gather_ops.argtypes = [vp]
     sig = [dp, C.c_int, dp, C.c_int, dp, dp, C.c_char_p]
     for name in MODELS:
         fn = getattr(L, name)
@@ -234,6 +248,12 @@ class Table:
     def set_option(self, key: str, value: int) -> None:
         _check(load_library().klp_set_option(self._h, key.encode(), int(value)), "klp_set_option")
 
+    def last_launch_info(self) -> str:
+        """Instantiation and mode of the most recent quadrature launch, e.g. 'k_quad<float, 1024, 1> splits=1 ring=0 ...'."""
+        buf = C.create_string_buffer(160)
+        _check(load_library().klp_last_launch_info(self._h, buf, len(buf)), "klp_last_launch_info")
+        return buf.value.decode()
+
     def arith_selftest(self, n_total: int, seed: int = 1):
         m = (C.c_ulonglong * 4)()
         _check(load_library().klp_arith_selftest(self._h, seed, int(n_total), m), "klp_arith_selftest")
@@ -245,10 +265,111 @@ class Table:
         return g.value
 
 
+# ---- several GPUs (include/klineprofiles_b200.h, klp_group_*) ---------------------------------------
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (rank 0 creates it, the host distributes it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().klp_nccl_unique_id(buf), "klp_nccl_unique_id")
+    return buf.raw
+
+
+def nccl_version() -> int:
+    v = C.c_int()
+    _check(load_library().klp_nccl_version(C.byref(v)), "klp_nccl_version")
+    return v.value
+
+
+def _vp_array(items):
+    return (C.c_void_p * len(items))(*[_ptr(x) for x in items])
+
+
+class Group:
+    """The GPUs that share a batch: table replicas, one per device (klp_group)."""
+
+    def __init__(self, handle, tables):
+        self._h = handle
+        self._tables = list(tables)   # borrowed by the C group: keep them alive
+        self.rank = None              # rank of this process in a one-process-per-GPU group
+        nl, nr = C.c_int(), C.c_int()
+        _check(load_library().klp_group_size(self._h, C.byref(nl), C.byref(nr)), "klp_group_size")
+        self.n_local, self.nranks = nl.value, nr.value
+
+    @classmethod
+    def local(cls, tables) -> "Group":
+        """One process drives len(tables) GPUs."""
+        arr = (C.c_void_p * len(tables))(*[t.handle for t in tables])
+        h = C.c_void_p()
+        _check(load_library().klp_group_create_local(arr, len(tables), C.byref(h)), "klp_group_create_local")
+        return cls(h, tables)
+
+    @classmethod
+    def from_rank(cls, table: Table, unique_id: bytes, rank: int, nranks: int) -> "Group":
+        """One process per GPU: this process is `rank` of `nranks`."""
+        h = C.c_void_p()
+        _check(load_library().klp_group_create_rank(table.handle, unique_id, int(rank), int(nranks), C.byref(h)),
+               "klp_group_create_rank")
+        g = cls(h, [table])
+        g.rank = int(rank)
+        return g
+
+    def close(self):
+        if self._h:
+            load_library().klp_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int) -> None:
+        _check(load_library().klp_group_set_option(self._h, key.encode(), int(value)), "klp_group_set_option")
+
+    def synchronize(self) -> None:
+        _check(load_library().klp_group_synchronize(self._h), "klp_group_synchronize")
+
+    def last_gather_ops(self) -> int:
+        return int(load_library().klp_group_last_gather_ops(self._h))
+
+    def eval_batch(self, model, params, energy, spectrum=None, precision: str = "f32", out=None) -> np.ndarray:
+        """Host numpy arrays in, [B, n] f64 out; the sets are sharded over the GPUs of a local group."""
+        m = _model_id(model)
+        params = np.ascontiguousarray(params, np.float64)
+        B = params.shape[0]
+        energy = np.ascontiguousarray(energy, np.float64)
+        n = energy.size - 1
+        per_set = 0
+        if spectrum is not None:
+            spectrum = np.ascontiguousarray(spectrum, np.float64)
+            per_set = int(spectrum.ndim == 2)
+        if out is None:
+            out = np.empty((B, n), np.float64)
+        _check(load_library().klp_group_eval_batch(self._h, m, PRECISIONS[precision], B, _dp(params), _dp(energy), n,
+                                                   _dp(spectrum), per_set, _dp(out)), "klp_group_eval_batch")
+        return out
+
+    def eval_allgather_device(self, model, d_params, d_energy, n_flux: int, d_out_all, B_local: int, d_spectrum=None,
+                              spectrum_per_set: bool = False, precision: str = "f32", streams=None) -> None:
+        """Device-resident shards in, every GPU holds all nranks * B_local spectra afterwards ([rank][set][bin]).
+        d_params / d_energy / d_out_all / d_spectrum / streams: one entry per local member."""
+        sp = _vp_array(d_spectrum) if d_spectrum is not None else None
+        st = _vp_array(streams) if streams is not None else None
+        _check(load_library().klp_group_eval_allgather_device(
+            self._h, _model_id(model), PRECISIONS[precision], int(B_local), _vp_array(d_params), _vp_array(d_energy), int(n_flux),
+            sp, int(spectrum_per_set), _vp_array(d_out_all), st), "klp_group_eval_allgather_device")
+
+
 # ---- the reference's model surface ---------------------------------------------------------------
 
+_INSTALLED = None   # the Table installed for the XSPEC symbols is kept alive here (the library does not own it)
+
+
 def set_default_table(table: Table | None) -> None:
+    global _INSTALLED
     load_library().klp_set_default_table(table.handle if table is not None else None)
+    _INSTALLED = table
 
 
 def set_legacy_precision(precision: str) -> None:

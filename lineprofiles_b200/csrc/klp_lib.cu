@@ -99,6 +99,12 @@ struct NvtxRange {
     ~NvtxRange() { nvtxRangePop(); }
 };
 
+// process-global state of the XSPEC symbols (xspec-wrapper.zig:57-68); defined here so that klp_table_destroy can
+// uninstall a table that is still referenced
+std::recursive_mutex g_legacy_mu;
+klp_table* g_default_table = nullptr;  // installed by the caller (not owned)
+klp_table* g_owned_table = nullptr;    // lazily loaded singleton (xspec-wrapper.zig:61)
+
 struct EvalExtra {
     bool use_limits = false;
     double lim_lo = 0, lim_hi = 0;
@@ -116,6 +122,8 @@ struct klp_table {
     float* d_frames = nullptr;
     float* d_spins = nullptr;
     float* d_mus = nullptr;
+    unsigned char* d_frame_ok = nullptr;   // per frame: values within the binades that license the FAST arithmetic (klp_kernels.cuh)
+    size_t frames_fast = 0;                // how many frames pass
     int sm_count = 0;
     int max_smem_optin = 0;
     int max_smem_sm = 0;
@@ -128,7 +136,6 @@ struct klp_table {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // options
     int quad_threads = 0;  // 0 = auto
-    bool fast_ok = false;  // table values within the binades that license the FAST arithmetic (klp_kernels.cuh)
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
@@ -147,7 +154,9 @@ struct klp_table {
     size_t ev_next = 0;
     double ms[4] = {0, 0, 0, 0};
     long launches[4] = {0, 0, 0, 0};
-    std::mutex mu_;
+    std::recursive_mutex mu_;   // guards the host-side state of the table (workspaces, options, setup cache, timing events)
+    // what the last quadrature launch was (klp_last_launch_info): instantiation and mode
+    char quad_variant[96] = "";
 };
 
 namespace {
@@ -222,6 +231,8 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     }
     k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
     KLP_CUDA(cudaGetLastError());
+    std::snprintf(t->quad_variant, sizeof(t->quad_variant), "k_quad<%s, %d, %d> splits=%d ring=%d", sizeof(T) == 4 ? "float" : "double", NT,
+                  FRAME_SMEM ? 1 : 0, splits, q.ring_mode);
     return KLP_OK;
 }
 
@@ -252,9 +263,6 @@ template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st
     switch (nt) {
         case 256: return launch_quad_nt<T, 256>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);
-#ifdef KLP_EXPERIMENT_NT
-        case KLP_EXPERIMENT_NT: return launch_quad_nt<T, KLP_EXPERIMENT_NT>(t, q, st);
-#endif
         case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
     return fail(KLP_ERR_ARG, "quad_threads must be 256, 512 or 1024");
@@ -270,6 +278,7 @@ TableDev table_dev(const klp_table* t) {
     d.n_mu = t->n_mu;
     d.n_r = t->n_r;
     d.n_g = t->n_g;
+    d.frame_ok = t->d_frame_ok;
     return d;
 }
 
@@ -324,7 +333,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.splits = 1;
         q.fine = (T*)t->fine.p;
         q.scratch = nullptr;
-        q.allow_fast = (t->fast_ok && t->use_fast) ? 1 : 0;
+        q.allow_fast = t->use_fast ? 1 : 0;
         q.one = 1.0f;
         q.counter = (unsigned long long*)t->counter.p + c;
         q.use_limits = ex.use_limits ? 1 : 0;
@@ -364,6 +373,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
                 r.out = d_out + (size_t)off * n_flux;
                 r.out_stride = (size_t)n_flux;
             }
+            r.caller_edges = conv ? 0 : 1;
             r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
             k_rebin<T><<<(unsigned)nb, 256, sizeof(double) * (size_t)r.n_stage, st>>>(r);
             KLP_CUDA(cudaGetLastError());
@@ -382,6 +392,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             ca.per_set = per_set;
             ca.n = n_flux;
             ca.out = d_out + (size_t)off * n_flux;
+            ca.regular = &cc_ptr<T>(t)->edges_regular;
             dim3 grid((unsigned)((n_flux + kConvThreads - 1) / kConvThreads), (unsigned)nb);
             // gridDim.y limit is 65535
             if (nb > 65535) return fail(KLP_ERR_ARG, "chunk must be <= 65535 for convolution models");
@@ -409,9 +420,9 @@ int eval_device(klp_table* t, int model, int precision, long long B, const doubl
     if (B == 0) return KLP_OK;
     if (!d_params || !d_energy || (!d_out && !stop_after_profile)) return fail(KLP_ERR_ARG, "null buffer");
     if (model >= 2 && !d_spec && !stop_after_profile) return fail(KLP_ERR_ARG, "convolution models need an input spectrum");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);   // host-side bookkeeping only; the device work is ordered by the caller's stream
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
-    if (t->timing) { t->ev_next = 0; t->ev_used.clear(); }
     if (!ex.setup_valid) t->setup_precision = -1;   // k_setup is about to overwrite the per-call constants
     if (precision == KLP_F32)
         return eval_device_t<float>(t, model, B, d_params, d_energy, n_flux, d_spec, per_set, d_out, st, ex, stop_after_profile);
@@ -443,9 +454,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     if (!params || !energy || !out) return fail(KLP_ERR_ARG, "null buffer");
     const bool conv = model >= 2;
     if (conv && !spectrum) return fail(KLP_ERR_ARG, "convolution models need an input spectrum");
-    for (int i = 0; i < n_flux; ++i)
-        if (!(energy[i + 1] > energy[i])) return fail(KLP_ERR_ARG, "energy edges must be strictly ascending");
-    std::lock_guard<std::mutex> lk(t->mu_);
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
     NvtxRange nvtx_call("klp_eval_batch");
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
@@ -468,7 +477,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     // staging chunk: t->stage_mb of output per slot (two slots; default 128 MB).  Larger chunks amortise the idle tail of
     // every k_quad launch, smaller ones shorten the last, un-overlapped copy-out.
     long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
-    hc = std::max<long long>(256, std::min<long long>(hc, 65535));
+    hc = std::max<long long>(16, std::min<long long>(hc, 65535));   // (very wide grids: fewer sets per slot, not more pinned memory)
     hc = std::min(hc, B);
     const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux;
     const size_t par_bytes = sizeof(double) * (size_t)hc * P;
@@ -488,7 +497,6 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         pending_off[k] = -1;
         return KLP_OK;
     };
-    const bool saved_timing = t->timing;
     for (long long c = 0; c < n_chunks; ++c) {
         const int k = (int)(c & 1);
         const long long off = c * hc, nb = std::min(hc, B - off);
@@ -506,10 +514,8 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         EvalExtra e2 = ex;
         e2.want_lims = ex.want_lims && c == 0;
         e2.setup_valid = setup_cached || c > 0;
-        if (c > 0) t->timing = false;  // per-kernel timing covers the first staging chunk only
         rc = eval_device(t, model, precision, nb, (const double*)t->d_params[k].p, (const double*)t->d_energy.p, n_flux,
                          dspec, per_set, (double*)t->d_out[k].p, t->s_compute, e2);
-        t->timing = saved_timing;
         if (rc) return rc;
         KLP_CUDA(cudaEventRecord(t->ev_comp[k], t->s_compute));
         KLP_CUDA(cudaStreamWaitEvent(t->s_d2h, t->ev_comp[k], 0));
@@ -591,14 +597,25 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     if (cudaMalloc(&t->d_spins, sizeof(float) * n_a) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(spins)");
     if (cudaMalloc(&t->d_mus, sizeof(float) * n_mu) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(mus)");
     {
-        // operand-range precondition of the FAST arithmetic: branches in [2^-20, 2^20], g limits in [2^-10, 2^10]
-        bool ok = true;
-        const size_t nb = F * (size_t)n_r * n_g, nr = F * (size_t)n_r;
-        for (size_t i = 0; i < nb && ok; ++i)
-            ok = upper[i] >= 9.5367431640625e-07f && upper[i] <= 1048576.f && lower[i] >= 9.5367431640625e-07f && lower[i] <= 1048576.f;
-        for (size_t i = 0; i < nr && ok; ++i)
-            ok = gmin[i] >= 0.0009765625f && gmin[i] <= 1024.f && gmax[i] >= 0.0009765625f && gmax[i] <= 1024.f;
-        t->fast_ok = ok;
+        // operand-range precondition of the FAST arithmetic, per frame: branches in [2^-20, 2^20], g limits in [2^-10, 2^10].
+        // A set may use the FAST sequences when its four frames pass (the reference zero-fills missing radii: one such
+        // frame must not slow down the whole table).
+        std::vector<unsigned char> okv(F, 1);
+        for (size_t f = 0; f < F; ++f) {
+            bool ok = true;
+            const float* u = upper + f * (size_t)n_r * n_g;
+            const float* l = lower + f * (size_t)n_r * n_g;
+            for (size_t i = 0; i < (size_t)n_r * n_g && ok; ++i)
+                ok = u[i] >= 9.5367431640625e-07f && u[i] <= 1048576.f && l[i] >= 9.5367431640625e-07f && l[i] <= 1048576.f;
+            const float* gn = gmin + f * n_r;
+            const float* gx = gmax + f * n_r;
+            for (int i = 0; i < n_r && ok; ++i)
+                ok = gn[i] >= 0.0009765625f && gn[i] <= 1024.f && gx[i] >= 0.0009765625f && gx[i] <= 1024.f;
+            okv[f] = ok ? 1 : 0;
+            t->frames_fast += ok ? 1 : 0;
+        }
+        if (cudaMalloc(&t->d_frame_ok, F) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(frame flags)");
+        if (cudaMemcpy(t->d_frame_ok, okv.data(), F, cudaMemcpyHostToDevice) != cudaSuccess) return bail(KLP_ERR_CUDA, "cudaMemcpy(frame flags)");
     }
     // pack frames: radii | gmin | gmax | upper | lower, padded to the stride; staged in slabs
     const size_t slab_frames = std::max<size_t>(1, (64u << 20) / (sizeof(float) * t->frame_stride));
@@ -746,7 +763,7 @@ bool fits_column(FILE* f, const FitsHdu& h, size_t col, std::vector<float>& out,
 
 int load_fits_table(const char* path, int device, klp_table** out) {
     FILE* f = std::fopen(path, "rb");
-    if (!f) return fail(KLP_ERR_IO, std::string("cannot open table file: ") + path);
+    if (!f) return fail(KLP_ERR_NOTFOUND, std::string("cannot open table file: ") + path);
     std::vector<FitsHdu> hdus;
     std::string err;
     auto bad = [&](const std::string& m) { std::fclose(f); return fail(KLP_ERR_IO, std::string(path) + ": " + m); };
@@ -788,7 +805,7 @@ int klp_table_load(const char* path, int device, klp_table** out) {
     *out = nullptr;
     if (!path) return fail(KLP_ERR_ARG, "null path");
     FILE* f = std::fopen(path, "rb");
-    if (!f) return fail(KLP_ERR_IO, std::string("cannot open table file: ") + path);
+    if (!f) return fail(KLP_ERR_NOTFOUND, std::string("cannot open table file: ") + path);
     char magic[8];
     int32_t d[4];
     if (std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "SIMPLE  ", 8) == 0) {
@@ -823,12 +840,19 @@ int klp_table_load(const char* path, int device, klp_table** out) {
 
 void klp_table_destroy(klp_table* t) {
     if (!t) return;
+    {
+        // a table that is still installed for the XSPEC symbols must not dangle: uninstall it first
+        std::lock_guard<std::recursive_mutex> lk(g_legacy_mu);
+        if (g_default_table == t) g_default_table = nullptr;
+        if (g_owned_table == t) g_owned_table = nullptr;
+    }
     if (t->device >= 0) {
         DeviceGuard dg(t->device);
         cudaDeviceSynchronize();
         if (t->d_frames) cudaFree(t->d_frames);
         if (t->d_spins) cudaFree(t->d_spins);
         if (t->d_mus) cudaFree(t->d_mus);
+        if (t->d_frame_ok) cudaFree(t->d_frame_ok);
         for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done, &t->order,
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})
@@ -904,7 +928,7 @@ int klp_eval_debug(klp_table* t, int model, int precision, long B, const double*
     if (!t) return fail(KLP_ERR_ARG, "null table");
     const int P = model_nparams(model);
     if (P < 0 || B < 1 || n_flux < 1 || !params || !energy) return fail(KLP_ERR_ARG, "bad argument");
-    std::lock_guard<std::mutex> lk(t->mu_);
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(KLP_ERR_CUDA, "no usable CUDA device for this table (host-only table or device lost); there is no CPU path");
     if (B > t->chunk) return fail(KLP_ERR_ARG, "klp_eval_debug: B must fit one chunk");
@@ -914,8 +938,11 @@ int klp_eval_debug(klp_table* t, int model, int precision, long B, const double*
     auto cleanup = [&]() { dpar.release(); den.release(); dout.release(); };
     if ((rc = dpar.ensure(sizeof(double) * (size_t)B * P)) || (rc = den.ensure(sizeof(double) * (size_t)(n_flux + 1))) ||
         (rc = dout.ensure(sizeof(double) * (size_t)B * n_flux))) { cleanup(); return rc; }
-    cudaMemcpy(dpar.p, params, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice);
-    cudaMemcpy(den.p, energy, sizeof(double) * (size_t)(n_flux + 1), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(dpar.p, params, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(den.p, energy, sizeof(double) * (size_t)(n_flux + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cleanup();
+        return fail(KLP_ERR_CUDA, "klp_eval_debug: host-to-device copy failed");
+    }
     EvalExtra ex;
     rc = eval_device(t, model, precision, B, (const double*)dpar.p, (const double*)den.p, n_flux, nullptr, 0, (double*)dout.p,
                      t->s_compute, ex, /*stop_after_profile=*/true);
@@ -925,18 +952,21 @@ int klp_eval_debug(klp_table* t, int model, int precision, long B, const double*
     if (fine_out) {
         if (precision == KLP_F32) {
             std::vector<float> h((size_t)B * kFineG);
-            cudaMemcpy(h.data(), t->fine.p, sizeof(float) * h.size(), cudaMemcpyDeviceToHost);
+            if (cudaMemcpy(h.data(), t->fine.p, sizeof(float) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { cleanup(); return fail(KLP_ERR_CUDA, "klp_eval_debug: device-to-host copy failed"); }
             for (long s = 0; s < B; ++s)
                 for (int i = 0; i < kNFine; ++i) fine_out[(size_t)s * kNFine + i] = h[(size_t)s * kFineG + i];
         } else {
             std::vector<double> h((size_t)B * kFineG);
-            cudaMemcpy(h.data(), t->fine.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost);
+            if (cudaMemcpy(h.data(), t->fine.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { cleanup(); return fail(KLP_ERR_CUDA, "klp_eval_debug: device-to-host copy failed"); }
             for (long s = 0; s < B; ++s)
                 for (int i = 0; i < kNFine; ++i) fine_out[(size_t)s * kNFine + i] = h[(size_t)s * kFineG + i];
         }
     }
-    if (profile_out && model >= 2)
-        cudaMemcpy(profile_out, t->prof.p, sizeof(double) * (size_t)B * (kConvN - 1), cudaMemcpyDeviceToHost);
+    if (profile_out && model >= 2 &&
+        cudaMemcpy(profile_out, t->prof.p, sizeof(double) * (size_t)B * (kConvN - 1), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cleanup();
+        return fail(KLP_ERR_CUDA, "klp_eval_debug: device-to-host copy failed");
+    }
     cleanup();
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(KLP_ERR_CUDA, cudaGetErrorString(e));
@@ -964,12 +994,16 @@ int klp_blend_frames_device(klp_table* t, int precision, long B, const double* d
 
 int klp_set_timing(klp_table* t, int enable) {
     if (!t) return fail(KLP_ERR_ARG, "null table");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
     t->timing = enable != 0;
+    t->ev_next = 0;
+    t->ev_used.clear();
     return KLP_OK;
 }
 
 int klp_get_timing(klp_table* t, double* ms4, long* launches4) {
     if (!t) return fail(KLP_ERR_ARG, "null table");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
     DeviceGuard dg(t->device);
     for (int k = 0; k < 4; ++k) { t->ms[k] = 0; t->launches[k] = 0; }
     for (auto& u : t->ev_used) {
@@ -984,16 +1018,23 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4) {
         if (ms4) ms4[k] = t->ms[k];
         if (launches4) launches4[k] = t->launches[k];
     }
+    t->ev_next = 0;   // the next call starts a new accumulation period
+    t->ev_used.clear();
+    return KLP_OK;
+}
+
+int klp_last_launch_info(klp_table* t, char* buf, size_t len) {
+    if (!t || !buf || len == 0) return fail(KLP_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
+    std::snprintf(buf, len, "%s fast_frames=%zu/%zu", t->quad_variant, t->frames_fast, (size_t)t->n_a * t->n_mu);
     return KLP_OK;
 }
 
 int klp_set_option(klp_table* t, const char* key, long value) {
     if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
     std::string k(key);
     if (k == "quad_threads") {
-#ifdef KLP_EXPERIMENT_NT
-        if (value == KLP_EXPERIMENT_NT) { t->quad_threads = (int)value; return KLP_OK; }
-#endif
         if (value != 0 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
         t->quad_threads = (int)value;
     } else if (k == "splits") {
@@ -1077,9 +1118,6 @@ const char* kMsgPrefix = "kerrlineprofile: ";              // xspec-wrapper.zig:
 const char* kDataDirEnv = "KLINE_PROF_DATA_DIR";           // xspec-wrapper.zig:10
 const char* kModelFile = "kerr-transfer-functions.fits";   // MODELPATH, xspec-wrapper.zig:11
 const char* kModelFileFlat = "kerr-transfer-functions.klpt"; // flat-container twin (lineprofiles_b200/tableio.py)
-std::mutex g_legacy_mu;
-klp_table* g_default_table = nullptr;  // installed by the caller
-klp_table* g_owned_table = nullptr;    // lazily loaded singleton (xspec-wrapper.zig:61)
 int g_legacy_precision = KLP_F32;
 bool g_have_lims = false;              // Q2 ratchet state
 double g_lims[2] = {0, 0};
@@ -1101,7 +1139,7 @@ int legacy_table(klp_table** out) {
 }
 
 void legacy_call(int model, const double* energy, int n_flux, const double* params, double* flux) {
-    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_legacy_mu);
     klp_table* t = nullptr;
     int rc = legacy_table(&t);
     if (rc == KLP_OK) {
@@ -1125,7 +1163,7 @@ void legacy_call(int model, const double* energy, int n_flux, const double* para
         }
     }
     // xspec-wrapper.zig:361-372
-    if (rc == KLP_ERR_IO)
+    if (rc == KLP_ERR_NOTFOUND)   // only a missing file gets the reference's hint; a present but unreadable one reports the parser's message
         std::fprintf(stderr, "error: %sFailed to find table model. Set the %s environment variable to where %s is located\n",
                      kMsgPrefix, kDataDirEnv, kModelFile);
     else
@@ -1136,16 +1174,16 @@ void legacy_call(int model, const double* energy, int n_flux, const double* para
 }  // namespace
 
 void klp_set_default_table(klp_table* t) {
-    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_legacy_mu);
     g_default_table = t;
 }
 void klp_set_legacy_precision(int precision) {
-    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_legacy_mu);
     if (precision == KLP_F32 || precision == KLP_F64) g_legacy_precision = precision;
     g_have_lims = false;
 }
 void klp_legacy_reset(void) {
-    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_legacy_mu);
     g_have_lims = false;
 }
 
@@ -1166,3 +1204,5 @@ void kconv10(const double* energy, int n_flux, const double* params, int, double
 }
 
 }  // extern "C"
+
+#include "klp_group.inc"

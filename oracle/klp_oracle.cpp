@@ -55,9 +55,103 @@ constexpr double kGaussW[4] = {1.2948496616886969327061143267787e-01,
                                3.8183005050511894495036977548818e-01,
                                4.1795918367346938775510204081658e-01};
 
-template <class T> inline T t_pow(T x, T y) { return (T)std::pow((double)x, (double)y); }
-template <class T> inline T t_cos(T x) { return (T)std::cos((double)x); }
-template <class T> inline T t_log10(T x) { return (T)std::log10((double)x); }
+// ---- transcendental policy ---------------------------------------------------------------------
+// Default (mode 0): cos / pow / log10 evaluated in f64 and rounded to T -- the policy the CUDA path
+// shares.  The reference calls Zig's own std.math.pow(f32, ..), @cos, std.math.log10 on f32
+// (emissivity.zig:12,45,52-53,67-75; xspec-wrapper.zig:224-226), which are not correctly rounded
+// and cannot be run here.  The other modes exist ONLY for the sensitivity study
+// (tools/transcendental_sensitivity.py, tests/test_oracle.py): they bound how far a spectrum can
+// move when every transcendental result is off by a few ulps of T.
+//   1: +k ulps of T on every result      2: -k ulps      3: pseudo-random in [-k, +k] ulps (hash of the bits)
+//   4: the C library's T-precision functions (powf / cosf / log10f for T = float)
+//   5: pow by the algorithm of Zig's std/math/pow.zig (a port of Go's math.Pow: frexp, square-and-multiply
+//      for the integer part of y, exp(yf * log(x)) for the fraction, all in T; restated from the published
+//      algorithm, the Zig sources are not available here), cos / log10 as in mode 4
+std::atomic<int> g_tp_mode{0}, g_tp_k{0}, g_tp_mask{7};   // mask: 1 = pow, 2 = cos, 4 = log10 are subject to the policy
+
+template <class T> struct UlpBits;
+template <> struct UlpBits<float> { using I = int32_t; };
+template <> struct UlpBits<double> { using I = int64_t; };
+template <class T> inline T ulp_shift(T v, long k) {
+    if (k == 0 || !(v == v) || std::isinf(v) || v == (T)0) return v;
+    typename UlpBits<T>::I b;
+    std::memcpy(&b, &v, sizeof(T));
+    b += (typename UlpBits<T>::I)k;   // sign-magnitude encoding: the magnitude moves by k ulps for either sign
+    T r;
+    std::memcpy(&r, &b, sizeof(T));
+    return r;
+}
+template <class T> inline T tp_perturb(T v) {
+    const int mode = g_tp_mode.load(std::memory_order_relaxed);
+    if (mode < 1 || mode > 3) return v;
+    const long k = g_tp_k.load(std::memory_order_relaxed);
+    long d = k;
+    if (mode == 2) d = -k;
+    if (mode == 3) {
+        typename UlpBits<T>::I b;
+        std::memcpy(&b, &v, sizeof(T));
+        uint64_t h = (uint64_t)b * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+        d = (long)(h % (uint64_t)(2 * k + 1)) - k;
+    }
+    // move |v| by d ulps (for v < 0 the bit pattern grows with the magnitude as well)
+    return ulp_shift<T>(v, d);
+}
+inline float lib_pow(float x, float y) { return ::powf(x, y); }
+inline double lib_pow(double x, double y) { return std::pow(x, y); }
+inline float lib_cos(float x) { return ::cosf(x); }
+inline double lib_cos(double x) { return std::cos(x); }
+inline float lib_log10(float x) { return ::log10f(x); }
+inline double lib_log10(double x) { return std::log10(x); }
+inline float lib_exp(float x) { return ::expf(x); }
+inline double lib_exp(double x) { return std::exp(x); }
+inline float lib_log(float x) { return ::logf(x); }
+inline double lib_log(double x) { return std::log(x); }
+// pow(T, x, y) as Zig's std.math.pow / Go's math.Pow structure it, every operation in T.
+template <class T> inline T gostyle_pow(T x, T y) {
+    if (y == (T)0 || x == (T)1) return (T)1;
+    if (x != x || y != y) return std::numeric_limits<T>::quiet_NaN();
+    if (y == (T)1) return x;
+    if (x == (T)0 || std::isinf(x) || std::isinf(y)) return lib_pow(x, y);   // special values: any libm agrees
+    if (y == (T)0.5) return std::sqrt(x);
+    if (y == (T)-0.5) return (T)1 / std::sqrt(x);
+    T yi, yf = std::modf(std::fabs(y), &yi);
+    if (yf != (T)0 && x < (T)0) return std::numeric_limits<T>::quiet_NaN();
+    if (yi >= (T)(sizeof(T) == 4 ? 2147483648.0 : 9223372036854775808.0)) return lib_exp(y * lib_log(x));
+    T a1 = (T)1;
+    int ae = 0;
+    if (yf != (T)0) {
+        if (yf > (T)0.5) { yf -= (T)1; yi += (T)1; }
+        a1 = lib_exp(yf * lib_log(x));
+    }
+    int xe = 0;
+    T x1 = std::frexp(x, &xe);
+    for (long long i = (long long)yi; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) { ae += xe; break; }   // over/underflow: left to scalbn below
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < (T)0.5) { x1 += x1; xe -= 1; }
+    }
+    if (y < (T)0) { a1 = (T)1 / a1; ae = -ae; }
+    return std::ldexp(a1, ae);
+}
+template <class T> inline T t_pow(T x, T y) {
+    const int mode = (g_tp_mask.load(std::memory_order_relaxed) & 1) ? g_tp_mode.load(std::memory_order_relaxed) : 0;
+    if (mode == 4) return lib_pow(x, y);
+    if (mode == 5) return gostyle_pow<T>(x, y);
+    return mode ? tp_perturb<T>((T)std::pow((double)x, (double)y)) : (T)std::pow((double)x, (double)y);
+}
+template <class T> inline T t_cos(T x) {
+    const int mode = (g_tp_mask.load(std::memory_order_relaxed) & 2) ? g_tp_mode.load(std::memory_order_relaxed) : 0;
+    if (mode >= 4) return lib_cos(x);
+    return mode ? tp_perturb<T>((T)std::cos((double)x)) : (T)std::cos((double)x);
+}
+template <class T> inline T t_log10(T x) {
+    const int mode = (g_tp_mask.load(std::memory_order_relaxed) & 4) ? g_tp_mode.load(std::memory_order_relaxed) : 0;
+    if (mode >= 4) return lib_log10(x);
+    return mode ? tp_perturb<T>((T)std::log10((double)x)) : (T)std::log10((double)x);
+}
 
 // Zig's @min/@max (LLVM minnum/maxnum): the non-NaN operand wins.  Spelled out so the CUDA
 // path can use the very same expression.
@@ -607,6 +701,15 @@ orc_table* orc_table_create(const float* spins, int n_a, const float* mus, int n
 void orc_table_destroy(orc_table* h) { delete h; }
 
 int orc_model_nparams(int model) { return model_nparams(model); }
+
+// Sensitivity study only (see the policy comment at t_pow): mode 0 restores the default.
+void orc_set_transcendental_policy(int mode, int k_ulps, int mask) {
+    g_tp_mode.store(mode); g_tp_k.store(k_ulps < 0 ? 0 : k_ulps); g_tp_mask.store(mask & 7);
+}
+// pow under the current policy, for the unit tests of the policies themselves
+double orc_pow_probe(int precision, double x, double y) {
+    return precision == 0 ? (double)t_pow<float>((float)x, (float)y) : t_pow<double>(x, y);
+}
 
 size_t orc_table_index(const orc_table* h, size_t ia, size_t imu) { return table_index(h->t, ia, imu); }
 void orc_find_tables(const orc_table* h, const size_t* pi, size_t* out) { find_tables(h->t, pi, out); }

@@ -54,8 +54,38 @@ def lib():
         L.orc_eval_batch.restype = C.c_int
         L.orc_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, dp, dp, C.c_int, dp, C.c_int, dp,
                                      C.c_int, C.c_int, C.POINTER(C.c_uint64), dp, dp, C.c_int, dp]
+        L.orc_set_transcendental_policy.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.orc_set_transcendental_policy.restype = None
+        L.orc_pow_probe.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.orc_pow_probe.restype = C.c_double
         _lib = L
     return _lib
+
+
+TRANSCENDENTAL_POLICIES = {"default": 0, "plus": 1, "minus": 2, "random": 3, "libm_T": 4, "zig_style_pow": 5}
+
+
+class transcendental_policy:
+    """Context manager: evaluate cos / pow / log10 under another policy (sensitivity study only; see the
+    policy comment in klp_oracle.cpp).  The default -- f64 libm rounded to T -- is what the CUDA path shares."""
+
+    FUNCS = {"pow": 1, "cos": 2, "log10": 4}
+
+    def __init__(self, mode: str, k_ulps: int = 0, funcs=("pow", "cos", "log10")):
+        self.mode, self.k = TRANSCENDENTAL_POLICIES[mode], int(k_ulps)
+        self.mask = sum(self.FUNCS[f] for f in funcs)
+
+    def __enter__(self):
+        lib().orc_set_transcendental_policy(self.mode, self.k, self.mask)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_transcendental_policy(0, 0, 7)
+        return False
+
+
+def pow_probe(x, y, precision="f32"):
+    return float(lib().orc_pow_probe(PREC[precision], float(x), float(y)))
 
 
 def _dp(a):

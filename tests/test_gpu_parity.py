@@ -407,3 +407,152 @@ def test_setup_cache_across_calls(gpu_table):
     torch.cuda.synchronize()
     assert np.array_equal(fn(), want)
     assert np.array_equal(out.cpu().numpy(), ref["l2"][1])
+
+
+# ---- round 2: BASELINE configs 4 and 5 at their stated shapes, irregular caller grids, host pipeline chunks ----------
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_config4_kconv10_4096_log_bins(gpu_table, oracle_table, prec):
+    """BASELINE config 4 shape: kconv10 walkers (seed 20262) on the 4096-bin log grid with the shared E^-2 continuum,
+    default (reference-order) convolution, both precisions, against the oracle."""
+    E = syn.energy_grid_log(4096)
+    spec = syn.powerlaw_continuum(E)
+    p = syn.random_params("kconv10", 8, seed=20262)
+    got = gpu_table.eval_batch("kconv10", p, E, spectrum=spec, precision=prec)
+    want = oracle_table.eval_batch("kconv10", p, E, spectrum=spec, precision=prec, threads=os.cpu_count() or 1)["out"]
+    assert_parity(got, want, f"config 4 kconv10 4096 {prec}")
+    if prec == "f32":
+        assert np.array_equal(got, want), "f32: reference operation order end to end -> bit-identical"
+
+
+def test_config5_gigabyte_table():
+    """BASELINE config 5 shape: a table above 1 GB (96 x 64 frames of 450 radii x 48 g* knots = 1.02 GiB) resident in HBM:
+    32 random kline sets against the oracle in f32 and 8 in f64, and the stand-alone blend kernel against the oracle's
+    interpolate_parameters on the same table."""
+    import torch
+    tab = syn.make_table(96, 64, 450, 48)
+    nbytes = sum(tab[k].nbytes for k in ("radii", "gmin", "gmax", "upper", "lower"))
+    assert nbytes >= 1 << 30
+    gt = klp.Table.from_arrays(tab, 0)
+    ot = orc.OracleTable(tab)
+    try:
+        E = syn.energy_grid_linear(1000)
+        p = syn.random_params("kline", 32, seed=20259)
+        nt = os.cpu_count() or 1
+        got = gt.eval_batch("kline", p, E, precision="f32")
+        want = ot.eval_batch("kline", p, E, precision="f32", threads=nt)["out"]
+        assert_parity(got, want, "config 5 f32")
+        assert np.array_equal(got, want)
+        assert_parity(gt.eval_batch("kline", p[:8], E, precision="f64"),
+                      ot.eval_batch("kline", p[:8], E, precision="f64", threads=nt)["out"], "config 5 f64")
+        ai = np.ascontiguousarray(p[:16, :2])
+        n = tab["n_r"] * (2 * tab["n_g"] + 3)
+        out = torch.empty((16, n), dtype=torch.float32, device="cuda")
+        gt.blend_frames_device(torch.from_numpy(ai).cuda(), out, 16, precision="f32")
+        torch.cuda.synchronize()
+        g = out.cpu().numpy().astype(np.float64)
+        for s in range(16):
+            fr = ot.blend_frame(ai[s, 0], ai[s, 1], "f32")
+            w = np.concatenate([fr["radii"], fr["gmin"], fr["gmax"], fr["upper"].ravel(), fr["lower"].ravel()])
+            assert np.array_equal(g[s], w), s
+    finally:
+        gt.close()
+
+
+def _irregular_edge_sets(n):
+    rng = np.random.default_rng(5)
+    asc = np.sort(rng.uniform(0.3, 9.0, n + 1))
+    cases = {"descending": asc[::-1].copy(), "shuffled": rng.permutation(asc), "repeated": np.repeat(asc[: (n + 2) // 2], 2)[: n + 1].copy(),
+             "with_nan": asc.copy(), "negative_start": asc - 1.0, "zero_start": np.concatenate([[0.0], asc[1:]])}
+    cases["with_nan"][n // 2] = np.nan
+    return cases
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_irregular_caller_edges_compute_like_the_reference(gpu_table, oracle_table, prec):
+    """The reference evaluates whatever edges it is handed (its loops only scan).  Edges that are not strictly ascending
+    and positive switch k_rebin / k_conv from bisection to the reference's scans: same values, NaN pattern included."""
+    n = 48
+    p = syn.random_params("kline5", 3, seed=31)
+    pc = syn.random_params("kconv5", 3, seed=32)
+    for name, E in _irregular_edge_sets(n).items():
+        got = gpu_table.eval_batch("kline5", p, E, precision=prec)
+        want = oracle_table.eval_batch("kline5", p, E, precision=prec)["out"]
+        assert_parity(got, want, f"kline5 {name} {prec}")
+        spec = np.linspace(1.0, 2.0, n)
+        for mode in (0, 1):
+            gpu_table.set_option("conv_mode", mode)
+            try:
+                got = gpu_table.eval_batch("kconv5", pc, E, spectrum=spec, precision=prec)
+            finally:
+                gpu_table.set_option("conv_mode", 0)
+            want = oracle_table.eval_batch("kconv5", pc, E, spectrum=spec, precision=prec)["out"]
+            assert_parity(got, want, f"kconv5 {name} {prec} conv_mode {mode}")
+
+
+def test_host_pipeline_multiple_staging_chunks(gpu_table):
+    """stage_mb = 1 forces several staging chunks through the double-buffered pinned slots (three streams, slot reuse):
+    the result must equal the single-chunk evaluation bit for bit -- additive model and convolution with per-set spectra."""
+    B = 700
+    E = syn.energy_grid_linear(1000)
+    p = syn.random_params("kline5", B, seed=41)
+    one = gpu_table.eval_batch("kline5", p, E, precision="f32")
+    E2 = syn.energy_grid_log(600)
+    pc = syn.random_params("kconv", B, seed=42)
+    spec = np.random.default_rng(43).uniform(0.5, 1.5, (B, 600))
+    one_c = gpu_table.eval_batch("kconv", pc, E2, spectrum=spec, precision="f32")
+    gpu_table.set_option("stage_mb", 1)
+    try:
+        assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), one)        # 131 sets per slot: 6 chunks
+        assert np.array_equal(gpu_table.eval_batch("kconv", pc, E2, spectrum=spec, precision="f32"), one_c)
+    finally:
+        gpu_table.set_option("stage_mb", 128)
+
+
+def test_installed_table_closed_then_xspec_symbol_zero_fills(table_arrays, capfd):
+    """A table that is destroyed while still installed for the XSPEC symbols is uninstalled by the library: the next call
+    takes the reference's error path (message + zero-filled output, xspec-wrapper.zig:361-372), no dangling pointer."""
+    t = klp.Table.from_arrays(table_arrays, device=0)
+    klp.set_default_table(t)
+    E = syn.energy_grid_linear(50)
+    old = os.environ.get("KLINE_PROF_DATA_DIR")
+    os.environ["KLINE_PROF_DATA_DIR"] = "/nonexistent-klp-dir"
+    try:
+        assert klp.kline(E, syn.CONFIG1_PARAMS).sum() > 0
+        t.close()
+        flux = np.full(50, 7.0)
+        klp.kline(E, syn.CONFIG1_PARAMS, flux)
+        assert np.all(flux == 0.0)
+        err = capfd.readouterr().err
+        assert "kerrlineprofile: " in err and "MODEL OUTPUT SET TO ZERO" in err and "KLINE_PROF_DATA_DIR" in err
+    finally:
+        klp.set_default_table(None)
+        klp.legacy_reset()
+        if old is None:
+            del os.environ["KLINE_PROF_DATA_DIR"]
+        else:
+            os.environ["KLINE_PROF_DATA_DIR"] = old
+
+
+def test_table_with_zeroed_rows_keeps_fast_path_elsewhere(oracle_table, table_arrays):
+    """The reference zero-fills radii a frame does not cover.  Frames holding such rows fail the operand-range check of the
+    branch-free arithmetic; only sets that blend one of THOSE frames take the plain-intrinsic path, and either way the
+    values equal the oracle's."""
+    tab = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in table_arrays.items()}
+    n_mu = tab["n_mu"]
+    for f in (3 * n_mu + 5, 3 * n_mu + 6, 17 * n_mu + 11):
+        tab["upper"][f, :4] = 0.0
+        tab["lower"][f, :4] = 0.0
+    gt = klp.Table.from_arrays(tab, 0)
+    ot = orc.OracleTable(tab)
+    try:
+        E = syn.energy_grid_linear(1000)
+        p = syn.random_params("kline5", 96, seed=51)
+        p[:8, 0] = tab["spins"][3] - 1e-3          # sets that blend the zeroed frames
+        p[:8, 1] = np.rad2deg(np.arccos(tab["mus"][5])) - 0.3
+        got = gt.eval_batch("kline5", p, E, precision="f32")
+        want = ot.eval_batch("kline5", p, E, precision="f32", threads=os.cpu_count() or 1)["out"]
+        assert np.array_equal(got, want, equal_nan=True)
+        assert "fast_frames=597/600" in gt.last_launch_info()
+    finally:
+        gt.close()

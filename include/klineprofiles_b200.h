@@ -82,6 +82,12 @@ void klp_table_destroy(klp_table* t);
 
 /* dims[4] = {n_a, n_mu, n_r, n_g} */
 int klp_table_dims(const klp_table* t, int* dims);
+/* What the table holds (diagnostics; this is how the tests check the FITS reader): the two parameter axes
+ * (spins[n_a], mus[n_mu]; either may be NULL) and one frame in the library's layout
+ * radii[n_r] gmin[n_r] gmax[n_r] upper[n_r][n_g] lower[n_r][n_g] (copied back from the device for
+ * device-resident tables). */
+int klp_table_parameters(const klp_table* t, float* spins, float* mus);
+int klp_table_read_frame(const klp_table* t, size_t frame, float* out);
 
 /* Host-side index logic, mirrors of line-profile.zig:60-70, :72-93, :209-231, :196-207. */
 size_t klp_table_index(const klp_table* t, size_t i_a, size_t i_mu);

@@ -50,6 +50,8 @@ def load_library():
     L.klp_table_destroy.argtypes = [vp]
     L.klp_table_destroy.restype = None
     L.klp_table_dims.argtypes = [vp, C.POINTER(C.c_int)]
+    L.klp_table_parameters.argtypes = [vp, fp, fp]
+    L.klp_table_read_frame.argtypes = [vp, C.c_size_t, fp]
     L.klp_table_index.argtypes = [vp, C.c_size_t, C.c_size_t]
     L.klp_table_index.restype = C.c_size_t
     L.klp_find_parameter_indices.argtypes = [vp, C.c_float, C.c_float, zp]
@@ -165,6 +167,21 @@ class Table:
     @property
     def frame_len(self) -> int:
         return self.n_r * (2 * self.n_g + 3)
+
+    def parameters(self):
+        """(spins[n_a], mus[n_mu]) as the table holds them."""
+        a, m = np.empty(self.n_a, np.float32), np.empty(self.n_mu, np.float32)
+        _check(load_library().klp_table_parameters(self._h, _fp(a), _fp(m)), "klp_table_parameters")
+        return a, m
+
+    def read_frame(self, frame: int) -> dict:
+        """One frame as the table holds it: radii/gmin/gmax [n_r], upper/lower [n_r, n_g]."""
+        buf = np.empty(self.frame_len, np.float32)
+        _check(load_library().klp_table_read_frame(self._h, int(frame), _fp(buf)), "klp_table_read_frame")
+        n_r, n_g = self.n_r, self.n_g
+        return dict(radii=buf[:n_r].copy(), gmin=buf[n_r:2 * n_r].copy(), gmax=buf[2 * n_r:3 * n_r].copy(),
+                    upper=buf[3 * n_r:3 * n_r + n_r * n_g].reshape(n_r, n_g).copy(),
+                    lower=buf[3 * n_r + n_r * n_g:].reshape(n_r, n_g).copy())
 
     # ---- index logic (line-profile.zig:60-93,196-231)
     def table_index(self, i_a: int, i_mu: int) -> int:

@@ -119,6 +119,7 @@ struct klp_table {
     int n_a = 0, n_mu = 0, n_r = 0, n_g = 0;
     size_t frame_stride = 0;
     std::vector<float> spins, mus;
+    std::vector<float> h_frames;   // host-only tables (device == -1) keep their packed frames for klp_table_read_frame
     float* d_frames = nullptr;
     float* d_spins = nullptr;
     float* d_mus = nullptr;
@@ -571,6 +572,16 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
         t->spins.assign(spins, spins + n_a);
         t->mus.assign(mus, mus + n_mu);
         t->frame_stride = (frame_len + 3) & ~(size_t)3;
+        const size_t F = (size_t)n_a * n_mu;
+        t->h_frames.assign(F * t->frame_stride, 0.f);
+        for (size_t f = 0; f < F; ++f) {
+            float* dst = t->h_frames.data() + f * t->frame_stride;
+            std::memcpy(dst, radii + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + n_r, gmin + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + 2 * (size_t)n_r, gmax + f * n_r, sizeof(float) * n_r);
+            std::memcpy(dst + 3 * (size_t)n_r, upper + f * (size_t)n_r * n_g, sizeof(float) * (size_t)n_r * n_g);
+            std::memcpy(dst + 3 * (size_t)n_r + (size_t)n_r * n_g, lower + f * (size_t)n_r * n_g, sizeof(float) * (size_t)n_r * n_g);
+        }
         *out = t;
         return KLP_OK;
     }
@@ -681,6 +692,7 @@ bool fits_parse(FILE* f, std::vector<FitsHdu>& hdus, std::string& err) {
                     else if (key != "XTENSION") { err = "bad FITS extension header"; return false; }
                     if (key == "XTENSION") h.bintable = val.find("BINTABLE") != std::string::npos;
                 }
+                else if (!end && (key == "XTENSION" || key == "SIMPLE")) { err = "FITS header without END card (the next HDU starts inside it)"; return false; }
                 if (key == "END") { end = true; continue; }
                 if (end || card[8] != '=') continue;
                 auto num = [&]() { return std::strtol(val.c_str(), nullptr, 10); };
@@ -875,6 +887,27 @@ void klp_table_destroy(klp_table* t) {
 int klp_table_dims(const klp_table* t, int* dims) {
     if (!t || !dims) return fail(KLP_ERR_ARG, "null argument");
     dims[0] = t->n_a; dims[1] = t->n_mu; dims[2] = t->n_r; dims[3] = t->n_g;
+    return KLP_OK;
+}
+
+int klp_table_parameters(const klp_table* t, float* spins, float* mus) {
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    if (spins) std::memcpy(spins, t->spins.data(), sizeof(float) * t->spins.size());
+    if (mus) std::memcpy(mus, t->mus.data(), sizeof(float) * t->mus.size());
+    return KLP_OK;
+}
+
+int klp_table_read_frame(const klp_table* t, size_t frame, float* out) {
+    if (!t || !out) return fail(KLP_ERR_ARG, "null argument");
+    const size_t F = (size_t)t->n_a * t->n_mu, len = (size_t)t->n_r * (2 * t->n_g + 3);
+    if (frame >= F) return fail(KLP_ERR_ARG, "frame index out of range");
+    if (t->device < 0) {
+        std::memcpy(out, t->h_frames.data() + frame * t->frame_stride, sizeof(float) * len);
+        return KLP_OK;
+    }
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(KLP_ERR_CUDA, "cannot select the table's device");
+    KLP_CUDA(cudaMemcpy(out, t->d_frames + frame * t->frame_stride, sizeof(float) * len, cudaMemcpyDeviceToHost));
     return KLP_OK;
 }
 

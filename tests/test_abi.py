@@ -170,3 +170,95 @@ def test_c99_client_links_and_gets_the_xspec_error_convention(tmp_path):
     assert run.returncode == 0
     assert run.stdout.split() == ["6", "16", "0", "0"]
     assert "kerrlineprofile: " in run.stderr and "MODEL OUTPUT SET TO ZERO" in run.stderr
+
+
+# ---- round 2: the FITS reader against a fixture it did not write ----------------------------------------------------
+
+def _fixture():
+    import importlib.util
+    p = os.path.join(os.path.dirname(__file__), "golden", "make_fits_fixture.py")
+    spec = importlib.util.spec_from_file_location("make_fits_fixture", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_fits_fixture_is_reproducible():
+    m = _fixture()
+    assert open(m.PATH, "rb").read() == m.build(), "tests/golden/fixture_table.fits is stale: rerun make_fits_fixture.py"
+
+
+def test_fits_reader_loads_the_hand_written_fixture():
+    """io.zig:53-87 reads HDU 2 column 1 (spins), HDU 3 column 1 (cos i) and columns 1-5 of every HDU from 4 on.  The fixture
+    is written from the FITS standard by tests/golden/make_fits_fixture.py (not by tableio.save_fits): '30E' vector columns
+    with TDIM, D-typed scalar columns, an extra J column, EXTNAME/COMMENT/HISTORY cards, two-block frame headers."""
+    m = _fixture()
+    want = m.fixture_arrays()
+    t = klp.Table.load(m.PATH, device=-1)
+    assert (t.n_a, t.n_mu, t.n_r, t.n_g) == (want["n_a"], want["n_mu"], want["n_r"], want["n_g"])
+    a, mu = t.parameters()
+    assert np.array_equal(a, want["spins"]) and np.array_equal(mu, want["mus"])
+    for f in range(t.n_a * t.n_mu):
+        fr = t.read_frame(f)
+        for k in ("radii", "gmin", "gmax", "upper", "lower"):
+            assert np.array_equal(fr[k], want[k][f]), (f, k)
+    assert t.find_parameter_indices(0.7, 0.5) == [2, 1] and t.find_tables([2, 1]) == [3, 5, 2, 4]
+    t.close()
+
+
+def test_fits_reader_rejects_corrupted_files(tmp_path):
+    m = _fixture()
+    good = m.build()
+
+    def load(b, name):
+        p = tmp_path / name
+        p.write_bytes(b)
+        return klp.Table.load(str(p), device=-1)
+
+    load(good, "good.fits").close()
+    with pytest.raises(klp.KlpError, match="truncated"):                      # cut inside the last frame's data
+        load(good[:-2880 - 100], "cut.fits")
+    with pytest.raises(klp.KlpError, match="NAXIS1"):                         # a column format that no longer adds up
+        load(good.replace(b"TFORM5  = '30E     '", b"TFORM5  = '29E     '", 1), "width.fits")
+    with pytest.raises(klp.KlpError, match="unsupported TFORM"):
+        load(good.replace(b"TFORM4  = '30E     '", b"TFORM4  = '30C     '", 1), "tform.fits")
+    frame_bytes = 2 * 2880 + 2880                                             # one frame HDU fewer than n_a * n_mu
+    with pytest.raises(klp.KlpError, match="n_spins"):
+        load(good[:-frame_bytes], "short.fits")
+    with pytest.raises(klp.KlpError, match="without END"):                    # primary END card wiped out: the next HDU would be swallowed
+        load(good[:2880].replace(b"END" + b" " * 77, b" " * 80) + good[2880:], "noend.fits")
+    with pytest.raises(klp.KlpError, match="floating point"):                 # spins column turned into integers
+        load(good.replace(b"TFORM1  = '1D      '", b"TFORM1  = '1K      '", 1), "ints.fits")
+    with pytest.raises(klp.KlpError) as ei:                                   # a missing file is a different status
+        klp.Table.load(str(tmp_path / "absent.fits"), device=-1)
+    assert "status 5" in str(ei.value)
+
+
+def test_xspec_static_archive_links_like_the_reference_package(tmp_path):
+    """The XSPEC package absorbs a STATIC archive named libxsklineprofiles.a (/root/reference/Makefile:43-48,61-72).  Ours is
+    built from the same object as the shared library; a plain C client links it with the line xspec/Makefile puts into the
+    generated package Makefile and gets the same behaviour."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    arch = os.path.join(root, "xspec", "libxsklineprofiles.a")
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/lib64/libcudart_static.a"):
+        pytest.skip("no g++ / static CUDA runtime")
+    assert os.path.exists(arch), "run __graft_entry__.build() (or make -C xspec lib)"
+    syms = subprocess.run(["nm", "-g", "--defined-only", arch], capture_output=True, text=True).stdout
+    for name in ("kline", "kline5", "kconv", "kconv5", "kconv10"):
+        assert f" T {name}\n" in syms, name
+    src = tmp_path / "client.c"
+    src.write_text('#include "klineprofiles_b200.h"\n#include <stdio.h>\nint main(void) { double e[3] = {1, 2, 3}, p[5] = {0.5, 30, 1.0, 400.0, 3.0}, '
+                   'f[2] = {7, 7}; kconv(e, 2, p, 0, f, 0, ""); printf("%g %g\\n", f[0], f[1]); return 0; }\n')
+    obj, exe = tmp_path / "client.o", tmp_path / "client"
+    assert subprocess.run(["gcc", "-std=c99", "-c", "-I", os.path.join(root, "include"), str(src), "-o", str(obj)]).returncode == 0
+    ln = subprocess.run(["g++", str(obj), "-o", str(exe), "-L", os.path.dirname(arch), "-l:libxsklineprofiles.a", "-L/usr/local/cuda/lib64",
+                         "-lcudart_static", "-ldl", "-lrt", "-lpthread"], capture_output=True, text=True)
+    assert ln.returncode == 0, ln.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, KLINE_PROF_DATA_DIR=str(tmp_path / "nowhere")))
+    assert run.returncode == 0 and run.stdout.split() == ["0", "0"]
+    assert "kerrlineprofile: " in run.stderr and "MODEL OUTPUT SET TO ZERO" in run.stderr
+    # the smoke script skips cleanly where HEASoft is absent
+    sm = subprocess.run([os.path.join(root, "tools", "xspec_smoke.sh")], capture_output=True, text=True)
+    assert sm.returncode in (0, 77), sm.stdout + sm.stderr

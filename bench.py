@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch", type=int, default=100000, help="parameter sets per GPU per step")
     ap.add_argument("--gather-chunk", type=int, default=0, help="sets per compute/gather chunk for N > 1 (0 = library default)")
+    ap.add_argument("--gather-tail", type=int, default=-1, help="sets of the final, un-overlapped chunk for N > 1 (-1 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the bounded block with BASELINE configs 1, 3 and 5")
@@ -363,6 +364,8 @@ def main():
         group = klp.Group.local(tables)
     if group is not None and args.gather_chunk > 0:
         group.set_option("gather_chunk", args.gather_chunk)
+    if group is not None and args.gather_tail >= 0:
+        group.set_option("gather_tail", args.gather_tail)
     energy = syn.energy_grid_linear(N_BINS)
     P = klp.NPARAMS[MODEL]
     # a different parameter batch every step and GPU (nothing can be reused from a previous step)

@@ -196,9 +196,10 @@ int klp_group_eval_batch(klp_group* g, int model, int precision, long B, const d
 /* Device-resident buffers: member i (i < n_local) evaluates the B_local sets of d_params[i] -- rank r of
  * the group owns the global sets [r * B_local, (r+1) * B_local) -- and EVERY member ends up with all
  * nranks * B_local spectra in d_out_all[i], laid out [rank][set][bin].  The batch is processed in chunks
- * (option "gather_chunk", default 16384 sets): while chunk k+1 is integrated, the spectra of chunk k
- * travel over NVLink on a second, high-priority stream -- one grouped NCCL operation per chunk (a single
- * ncclAllGather when the batch is one chunk).  Arrays have n_local entries; d_spectrum may be NULL for
+ * (options "gather_chunk", default 65535 sets = the kernel's launch cap, and "gather_tail", default 4096
+ * sets for the final chunk): while chunk k+1 is integrated, the spectra of chunk k travel over NVLink on
+ * a second, high-priority stream -- one grouped NCCL operation per chunk (a single ncclAllGather when the
+ * batch is one chunk); only the short final chunk is gathered with nothing left to overlap.  Arrays have n_local entries; d_spectrum may be NULL for
  * kline / kline5; cuda_streams may be NULL (the group's own streams; see klp_group_synchronize).
  * Asynchronous: d_out_all[i] is complete in stream order on cuda_streams[i]. */
 int klp_group_eval_allgather_device(klp_group* g, int model, int precision, long B_local,

@@ -397,7 +397,19 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             dim3 grid((unsigned)((n_flux + kConvThreads - 1) / kConvThreads), (unsigned)nb);
             // gridDim.y limit is 65535
             if (nb > 65535) return fail(KLP_ERR_ARG, "chunk must be <= 65535 for convolution models");
-            if (t->conv_mode == 1) {
+            // CTAs per set: one when the batch fills the GPU (the per-set table is then built once), more for small batches
+            const long long fill = std::max<long long>(1, (4LL * t->sm_count + nb - 1) / nb);
+            if (t->conv_mode == 1) {          // cumulative-profile formulation
+                constexpr int EPL = 2;
+                const int chunks = (n_flux + 32 * EPL - 2) / (32 * EPL - 1);
+                const unsigned cps = (unsigned)std::max<long long>(1, std::min<long long>((chunks + 7) / 8, fill));
+                KLP_CUDA(cudaFuncSetAttribute(k_conv_cum<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvFastSmemBytes));
+                k_conv_cum<EPL><<<dim3(cps, (unsigned)nb), 256, kConvFastSmemBytes, st>>>(ca);
+            } else if (t->conv_mode == 0) {   // the reference's operation order (default)
+                const unsigned cps = (unsigned)std::max<long long>(1, std::min<long long>((n_flux + kConvXThreads - 1) / kConvXThreads, fill));
+                KLP_CUDA(cudaFuncSetAttribute(k_conv_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvXSmemBytes));
+                k_conv_exact<<<dim3(cps, (unsigned)nb), kConvXThreads, kConvXSmemBytes, st>>>(ca);
+            } else if (t->conv_mode == 3) {   // round-1 kernels, kept for A/B measurements
                 dim3 gridf((unsigned)((n_flux + kConvFastBinsPerCta - 1) / kConvFastBinsPerCta), (unsigned)nb);
                 KLP_CUDA(cudaFuncSetAttribute(k_conv_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvFastSmemBytes));
                 k_conv_fast<<<gridf, kConvFastThreads, kConvFastSmemBytes, st>>>(ca);
@@ -405,6 +417,9 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
                 KLP_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
                 k_conv<<<grid, kConvThreads, kConvSmemBytes, st>>>(ca);
             }
+            KLP_CUDA(cudaGetLastError());
+            // caller edges that are not strictly ascending and positive: the reference's own loops (returns at once otherwise)
+            k_conv_general<<<dim3((unsigned)std::min<long long>((n_flux + 255) / 256, fill), (unsigned)nb), 256, 0, st>>>(ca);
             KLP_CUDA(cudaGetLastError());
         }
     }
@@ -1083,7 +1098,7 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "frame_global") {
         t->frame_global = value != 0;
     } else if (k == "conv_mode") {
-        if (value < 0 || value > 1) return fail(KLP_ERR_ARG, "conv_mode");
+        if (value < 0 || value > 3) return fail(KLP_ERR_ARG, "conv_mode");
         t->conv_mode = (int)value;
     } else if (k == "fast") {
         t->use_fast = value != 0;

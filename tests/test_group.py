@@ -99,7 +99,7 @@ def test_two_gpu_local_group(table_arrays, gpu_table):
     try:
         E = syn.energy_grid_linear(1000)
         # host buffers: odd batch, shards of different length, no collective
-        p = syn.random_params("kline5", 4001, seed=64)
+        p = syn.random_params("kline5", 5001, seed=64)
         want = gpu_table.eval_batch("kline5", p, E, precision="f32")
         assert np.array_equal(g.eval_batch("kline5", p, E, precision="f32"), want)
         # device-resident: 2 x 2500 sets, chunks of 1000 -> several grouped broadcasts; then one chunk -> one all-gather
@@ -108,16 +108,17 @@ def test_two_gpu_local_group(table_arrays, gpu_table):
         Es = [torch.from_numpy(E).to(f"cuda:{d}") for d in (0, 1)]
         torch.cuda.synchronize(0)
         torch.cuda.synchronize(1)
-        for chunk, min_ops in ((1000, 3), (65535, 1)):
+        for chunk, tail, n_ops in ((1000, 4096, 3), (65535, 4096, 1), (65535, 300, 2)):   # [1000, 1000, 500]; one all-gather; [2200, 300]
             outs = [torch.zeros((2 * B, 1000), dtype=torch.float64, device=f"cuda:{d}") for d in (0, 1)]
             torch.cuda.synchronize(0)
             torch.cuda.synchronize(1)   # the group's own streams do not wait for torch's
             g.set_option("gather_chunk", chunk)
+            g.set_option("gather_tail", tail)
             g.eval_allgather_device("kline5", ps, Es, 1000, outs, B)
             g.synchronize()
-            assert g.last_gather_ops() >= min_ops
+            assert g.last_gather_ops() == n_ops
             for d in (0, 1):
-                assert np.array_equal(outs[d].cpu().numpy(), want[: 2 * B]), (chunk, d)
+                assert np.array_equal(outs[d].cpu().numpy(), want[: 2 * B]), (chunk, tail, d)
         # convolution model with per-set spectra
         E2 = syn.energy_grid_log(300)
         pc = syn.random_params("kconv", 600, seed=65)

@@ -146,7 +146,9 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 /* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default: 1024 in f32, 512 in f64), "splits" (CTAs
  * that share one set, 0 = auto: more than one only when the batch is smaller than the GPU), "conv_mode" (0 = the
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
- * faster, equal to rounding), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring and add them
+ * faster, equal to rounding), "coop" (1 = batches
+ * much smaller than the GPU use one cooperative k_quad launch whose CTAs share a set's ordered additions and rebin it (default), 0 = separate
+ * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring and add them
  * while evaluating: no DRAM traffic, ~4.5 % slower; default 0), "chunk" (sets per internal chunk), "stage_mb" (pinned staging per slot of the
  * host-buffer pipeline, default 128), "order" (1 = evaluate the costliest sets of a launch first (default), 0 = in input order), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -132,7 +133,7 @@ struct klp_table {
     Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done, order;
     // host-API staging
     Buf d_energy, d_spec, d_params[2], d_out[2], d_spec_slot[2];
-    PinBuf h_params[2], h_out[2], h_spec_slot[2];
+    PinBuf h_params[2], h_out[2], h_spec_slot[2], h_lims;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // options
@@ -145,6 +146,10 @@ struct klp_table {
     std::vector<double> setup_energy;
     int setup_precision = -1, setup_conv = -1;
     int stage_mb = 128;         // pinned staging per slot of the host pipeline (MB of output)
+    bool use_coop = true;       // option "coop": cooperative small-batch mode of k_quad (fused rebin) when the batch is tiny
+    bool coop_supported = false;
+    bool rebin_attr_set[2] = {false, false};
+    std::map<long long, int> quad_occ;   // (k_quad instantiation, shared memory) -> resident CTAs per SM
     bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
     long chunk = 65535;
@@ -191,13 +196,28 @@ template <> CallConsts<float>* cc_ptr<float>(klp_table* t) { return (CallConsts<
 template <> CallConsts<double>* cc_ptr<double>(klp_table* t) { return (CallConsts<double>*)t->cc64.p; }
 
 template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, QuadArgs<T>& q, size_t smem, size_t fb, cudaStream_t st) {
-    KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // attribute + occupancy of this instantiation: asked once per (instantiation, shared-memory size), not per launch
+    const long long key = ((long long)(sizeof(T) == 4 ? 0 : 1) << 60) | ((long long)NT << 40) | ((long long)(FRAME_SMEM ? 1 : 0) << 39) | (long long)smem;
     int occ = 0;
-    KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM>, NT, smem));
+    auto it = t->quad_occ.find(key);
+    if (it != t->quad_occ.end()) occ = it->second;
+    else {
+        KLP_CUDA(cudaFuncSetAttribute(k_quad<T, NT, FRAME_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<T, NT, FRAME_SMEM>, NT, smem));
+        t->quad_occ[key] = occ;
+    }
     if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
-    if (splits <= 0) {
+    // Cooperative small-batch mode: at most a quarter of the resident CTAs' worth of sets (a single XSPEC call is the extreme).
+    // Every CTA of the launch is resident, so the CTAs of a set may wait for each other: items of one radius, the ordered
+    // additions shared by bin group, the rebin fused into the last CTA (one kernel instead of two, ~3x shorter critical path).
+    bool coop = FRAME_SMEM && t->use_coop && t->coop_supported && splits <= 0 && q.B * 4 <= resident && !t->deposit_ring;
+    if (coop) {
+        splits = (int)std::min<long long>(resident / q.B, kMaxSplits);
+        coop = splits >= 2;
+    }
+    if (!coop && splits <= 0) {
         // CTAs sharing a set.  Sets differ in cost by a factor of ~2, so a batch of the order of the resident CTAs is
         // balanced by cutting every set into several (set, split) items (each split repeats the plan, ~3 % of a set);
         // measured optimum (tools/splits_probe.py): ~8 items per resident CTA, at most 16 splits (32 for a handful of sets).
@@ -208,6 +228,8 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     }
     splits = std::max(1, std::min(splits, kMaxSplits));
     q.splits = splits;
+    q.coop = coop ? 1 : 0;
+    q.item_radii = coop ? 1 : kItemRadii;
     const long long items = q.B * splits;
     const int grid = (int)std::min<long long>(items, resident);
     if (!FRAME_SMEM) {
@@ -230,10 +252,26 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * 2 * (size_t)q.B, st));
         q.done = (unsigned*)t->done.p;
     }
-    k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
+    if (coop) {
+        q.rb.n_stage = (int)std::min<size_t>(fb / sizeof(double), 1u << 20);   // doubles of the dead frame area the fused rebin may use
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_quad<T, NT, FRAME_SMEM>, (const QuadArgs<T>)q);
+        if (e != cudaSuccess) return fail(KLP_ERR_CUDA, std::string("cooperative k_quad launch: ") + cudaGetErrorString(e));
+    } else {
+        k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
+    }
     KLP_CUDA(cudaGetLastError());
-    std::snprintf(t->quad_variant, sizeof(t->quad_variant), "k_quad<%s, %d, %d> splits=%d ring=%d", sizeof(T) == 4 ? "float" : "double", NT,
-                  FRAME_SMEM ? 1 : 0, splits, q.ring_mode);
+    std::snprintf(t->quad_variant, sizeof(t->quad_variant), "k_quad<%s, %d, %d> splits=%d ring=%d coop=%d", sizeof(T) == 4 ? "float" : "double", NT,
+                  FRAME_SMEM ? 1 : 0, splits, q.ring_mode, q.coop);
     return KLP_OK;
 }
 
@@ -264,9 +302,12 @@ template <class T> int launch_quad(klp_table* t, QuadArgs<T>& q, cudaStream_t st
     switch (nt) {
         case 256: return launch_quad_nt<T, 256>(t, q, st);
         case 512: return launch_quad_nt<T, 512>(t, q, st);
+        case 768:   // f32 only: 24 warps with up to 85 registers each (tools/nt_probe.py)
+            if constexpr (sizeof(T) == 4) return launch_quad_nt<T, 768>(t, q, st);
+            else return fail(KLP_ERR_ARG, "quad_threads 768 is an f32 configuration");
         case 1024: return launch_quad_nt<T, 1024>(t, q, st);
     }
-    return fail(KLP_ERR_ARG, "quad_threads must be 256, 512 or 1024");
+    return fail(KLP_ERR_ARG, "quad_threads must be 256, 512, 768 or 1024");
 }
 
 TableDev table_dev(const klp_table* t) {
@@ -349,34 +390,41 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             KLP_CUDA(cudaGetLastError());
             q.order = (const int*)t->order.p;
         }
+        RebinArgs<T> r;
+        r.cc = cc_ptr<T>(t);
+        r.params = q.params;
+        r.model = model;
+        r.P = P;
+        r.B = nb;
+        r.fine = (const T*)t->fine.p;
+        if (conv) {
+            r.energy = (const double*)t->conv_grid.p;
+            r.n_out = kConvN - 1;
+            r.out = (double*)t->prof.p;
+            r.out_stride = kConvN - 1;
+        } else {
+            r.energy = d_energy;
+            r.n_out = n_flux;
+            r.out = d_out + (size_t)off * n_flux;
+            r.out_stride = (size_t)n_flux;
+        }
+        r.caller_edges = conv ? 0 : 1;
+        r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
+        q.rb = r;       // used by the cooperative small-batch mode, which rebins inside k_quad
+        q.coop = 0;
+        q.item_radii = kItemRadii;
         {
             NvtxRange nvtx_quad("klp integrate (k_quad)");
             TimedLaunch tl(t, st, 1);
             if ((rc = launch_quad<T>(t, q, st))) return rc;
         }
-        {
+        if (!q.coop) {
             TimedLaunch tl(t, st, 2);
-            RebinArgs<T> r;
-            r.cc = cc_ptr<T>(t);
-            r.params = q.params;
-            r.model = model;
-            r.P = P;
-            r.B = nb;
-            r.fine = (const T*)t->fine.p;
-            if (conv) {
-                r.energy = (const double*)t->conv_grid.p;
-                r.n_out = kConvN - 1;
-                r.out = (double*)t->prof.p;
-                r.out_stride = kConvN - 1;
-            } else {
-                r.energy = d_energy;
-                r.n_out = n_flux;
-                r.out = d_out + (size_t)off * n_flux;
-                r.out_stride = (size_t)n_flux;
+            if (!t->rebin_attr_set[sizeof(T) == 4 ? 0 : 1]) {
+                KLP_CUDA(cudaFuncSetAttribute(k_rebin<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rebin_smem_bytes<T>(4096)));
+                t->rebin_attr_set[sizeof(T) == 4 ? 0 : 1] = true;
             }
-            r.caller_edges = conv ? 0 : 1;
-            r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
-            k_rebin<T><<<(unsigned)nb, 256, sizeof(double) * (size_t)r.n_stage, st>>>(r);
+            k_rebin<T><<<(unsigned)nb, 256, rebin_smem_bytes<T>(r.n_stage), st>>>(r);
             KLP_CUDA(cudaGetLastError());
         }
         if (conv && !stop_after_profile) {
@@ -489,7 +537,8 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         if ((rc = t->d_spec.ensure(sizeof(double) * (size_t)n_flux))) return rc;
         KLP_CUDA(cudaMemcpyAsync(t->d_spec.p, spectrum, sizeof(double) * (size_t)n_flux, cudaMemcpyHostToDevice, t->s_compute));
     }
-    KLP_CUDA(cudaStreamSynchronize(t->s_compute));
+    // (no synchronisation needed here: copies from pageable memory are staged before cudaMemcpyAsync returns, and the kernels
+    // that read the grid / spectrum are enqueued on the same stream)
     // staging chunk: t->stage_mb of output per slot (two slots; default 128 MB).  Larger chunks amortise the idle tail of
     // every k_quad launch, smaller ones shorten the last, un-overlapped copy-out.
     long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
@@ -505,6 +554,40 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
             if ((rc = t->d_spec_slot[k].ensure(out_bytes)) || (rc = t->h_spec_slot[k].ensure(out_bytes))) return rc;
     }
     const long long n_chunks = (B + hc - 1) / hc;
+    if ((rc = t->h_lims.ensure(16))) return rc;
+    if (n_chunks == 1) {
+        // One staging chunk (the XSPEC call pattern is B = 1): everything on ONE stream, one synchronisation -- no events, no
+        // cross-stream waits; the radial-grid end points of the ratchet ride along with the spectra.
+        cudaStream_t s = t->s_compute;
+        std::memcpy(t->h_params[0].p, params, sizeof(double) * (size_t)B * P);
+        KLP_CUDA(cudaMemcpyAsync(t->d_params[0].p, t->h_params[0].p, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, s));
+        const double* dspec = (const double*)t->d_spec.p;
+        if (conv && per_set) {
+            std::memcpy(t->h_spec_slot[0].p, spectrum, sizeof(double) * (size_t)B * n_flux);
+            KLP_CUDA(cudaMemcpyAsync(t->d_spec_slot[0].p, t->h_spec_slot[0].p, sizeof(double) * (size_t)B * n_flux, cudaMemcpyHostToDevice, s));
+            dspec = (const double*)t->d_spec_slot[0].p;
+        }
+        EvalExtra e2 = ex;
+        e2.setup_valid = setup_cached;
+        rc = eval_device(t, model, precision, B, (const double*)t->d_params[0].p, (const double*)t->d_energy.p, n_flux, dspec, per_set,
+                         (double*)t->d_out[0].p, s, e2);
+        if (rc) return rc;
+        KLP_CUDA(cudaMemcpyAsync(t->h_out[0].p, t->d_out[0].p, sizeof(double) * (size_t)B * n_flux, cudaMemcpyDeviceToHost, s));
+        if (lims_out && ex.want_lims)
+            KLP_CUDA(cudaMemcpyAsync(t->h_lims.p, t->lims.p, precision == KLP_F32 ? sizeof(float) * 2 : sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+        KLP_CUDA(cudaStreamSynchronize(s));
+        std::memcpy(out, t->h_out[0].p, sizeof(double) * (size_t)B * n_flux);
+        if (lims_out && ex.want_lims) {
+            if (precision == KLP_F32) { lims_out[0] = ((const float*)t->h_lims.p)[0]; lims_out[1] = ((const float*)t->h_lims.p)[1]; }
+            else { lims_out[0] = ((const double*)t->h_lims.p)[0]; lims_out[1] = ((const double*)t->h_lims.p)[1]; }
+        }
+        if (!setup_cached) {   // remember what the per-call constants on the device belong to
+            t->setup_energy.assign(energy, energy + n_flux + 1);
+            t->setup_precision = precision;
+            t->setup_conv = conv ? 1 : 0;
+        }
+        return KLP_OK;
+    }
     long long pending_off[2] = {-1, -1}, pending_n[2] = {0, 0};
     auto drain = [&](int k) -> int {
         if (pending_off[k] < 0) return KLP_OK;
@@ -616,6 +699,7 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete t; return fail(KLP_ERR_CUDA, "cudaGetDeviceProperties"); }
     t->sm_count = prop.multiProcessorCount;
+    t->coop_supported = prop.cooperativeLaunch != 0;
     t->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     t->max_smem_sm = (int)prop.sharedMemPerMultiprocessor;
     auto bail = [&](int code, const std::string& m) { klp_table_destroy(t); return fail(code, m); };
@@ -884,7 +968,7 @@ void klp_table_destroy(klp_table* t) {
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})
             b->release();
-        for (PinBuf* b : {&t->h_params[0], &t->h_params[1], &t->h_out[0], &t->h_out[1], &t->h_spec_slot[0], &t->h_spec_slot[1]})
+        for (PinBuf* b : {&t->h_params[0], &t->h_params[1], &t->h_out[0], &t->h_out[1], &t->h_spec_slot[0], &t->h_spec_slot[1], &t->h_lims})
             b->release();
         if (t->s_compute) cudaStreamDestroy(t->s_compute);
         if (t->s_h2d) cudaStreamDestroy(t->s_h2d);
@@ -1083,7 +1167,7 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     std::lock_guard<std::recursive_mutex> lk(t->mu_);
     std::string k(key);
     if (k == "quad_threads") {
-        if (value != 0 && value != 256 && value != 512 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
+        if (value != 0 && value != 256 && value != 512 && value != 768 && value != 1024) return fail(KLP_ERR_ARG, "quad_threads");
         t->quad_threads = (int)value;
     } else if (k == "splits") {
         if (value < 0 || value > kMaxSplits) return fail(KLP_ERR_ARG, "splits");
@@ -1093,6 +1177,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "stage_mb") {
         if (value < 1 || value > 4096) return fail(KLP_ERR_ARG, "stage_mb");
         t->stage_mb = (int)value;
+    } else if (k == "coop") {
+        t->use_coop = value != 0;
     } else if (k == "deposit_ring") {
         t->deposit_ring = value != 0;
     } else if (k == "frame_global") {

@@ -67,6 +67,7 @@ def load_library():
     L.klp_get_timing.argtypes = [vp, dp, C.POINTER(C.c_long)]
     L.klp_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.klp_last_launch_info.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.klp_get_phase_times.argtypes = [vp, dp]
     L.klp_fma_peak_gflops.argtypes = [vp, C.c_int, dp]
     L.klp_arith_selftest.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     pvp = C.POINTER(vp)
@@ -270,6 +271,12 @@ class Table:
         buf = C.create_string_buffer(160)
         _check(load_library().klp_last_launch_info(self._h, buf, len(buf)), "klp_last_launch_info")
         return buf.value.decode()
+
+    def phase_times(self):
+        """Microseconds at which k_quad's first CTA passed its phase boundaries (option phase_clock = 1)."""
+        us = (C.c_double * 9)()
+        _check(load_library().klp_get_phase_times(self._h, us), "klp_get_phase_times")
+        return dict(zip(("start", "unpack", "grid_blend", "plan", "bin_ranges", "stage_a", "all_arrived", "additions", "rebin"), (float(v) for v in us)))
 
     def arith_selftest(self, n_total: int, seed: int = 1):
         m = (C.c_ulonglong * 4)()

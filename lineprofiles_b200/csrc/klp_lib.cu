@@ -130,7 +130,8 @@ struct klp_table {
     int max_smem_optin = 0;
     int max_smem_sm = 0;
     // workspaces
-    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done, order;
+    Buf cc32, cc64, fine, prof, conv_grid, conv_avg, scratch, counter, lims, vals, done, order, phase;
+    bool phase_clock = false;   // option "phase_clock": k_quad stamps %globaltimer at its phase boundaries (klp_get_phase_times)
     // host-API staging
     Buf d_energy, d_spec, d_params[2], d_out[2], d_spec_slot[2];
     PinBuf h_params[2], h_out[2], h_spec_slot[2], h_lims;
@@ -209,10 +210,10 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     if (occ < 1) return fail(KLP_ERR_CUDA, "k_quad does not fit on an SM");
     const long long resident = (long long)occ * t->sm_count;
     int splits = t->splits;
-    // Cooperative small-batch mode: at most a quarter of the resident CTAs' worth of sets (a single XSPEC call is the extreme).
+    // Cooperative small-batch mode: at least 16 CTAs per set (measured: faster up to ~9 sets on a B200; a single XSPEC call is the extreme).
     // Every CTA of the launch is resident, so the CTAs of a set may wait for each other: items of one radius, the ordered
     // additions shared by bin group, the rebin fused into the last CTA (one kernel instead of two, ~3x shorter critical path).
-    bool coop = FRAME_SMEM && t->use_coop && t->coop_supported && splits <= 0 && q.B * 4 <= resident && !t->deposit_ring;
+    bool coop = FRAME_SMEM && t->use_coop && t->coop_supported && splits <= 0 && q.B * 16 <= resident && !t->deposit_ring;
     if (coop) {
         splits = (int)std::min<long long>(resident / q.B, kMaxSplits);
         coop = splits >= 2;
@@ -230,6 +231,7 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     q.splits = splits;
     q.coop = coop ? 1 : 0;
     q.item_radii = coop ? 1 : kItemRadii;
+    q.item_subs = coop ? 4 : 1;
     const long long items = q.B * splits;
     const int grid = (int)std::min<long long>(items, resident);
     if (!FRAME_SMEM) {
@@ -383,6 +385,12 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.lim_hi = (T)ex.lim_hi;
         q.lims_out = (ex.want_lims && c == 0) ? (T*)t->lims.p : nullptr;
         q.order = nullptr;
+        q.phase_ns = nullptr;
+        if (t->phase_clock) {
+            if ((rc = t->phase.ensure(sizeof(unsigned long long) * 16))) return rc;
+            KLP_CUDA(cudaMemsetAsync(t->phase.p, 0, sizeof(unsigned long long) * 16, st));
+            q.phase_ns = (unsigned long long*)t->phase.p;
+        }
         if (nb >= 512 && t->use_order) {   // costliest sets first (k_order)
             if ((rc = t->order.ensure(sizeof(int) * (size_t)nb))) return rc;
             TimedLaunch tl(t, st, 0);   // accounted with the set-up kernels
@@ -413,6 +421,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.rb = r;       // used by the cooperative small-batch mode, which rebins inside k_quad
         q.coop = 0;
         q.item_radii = kItemRadii;
+        q.item_subs = 1;
         {
             NvtxRange nvtx_quad("klp integrate (k_quad)");
             TimedLaunch tl(t, st, 1);
@@ -964,7 +973,7 @@ void klp_table_destroy(klp_table* t) {
         if (t->d_spins) cudaFree(t->d_spins);
         if (t->d_mus) cudaFree(t->d_mus);
         if (t->d_frame_ok) cudaFree(t->d_frame_ok);
-        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done, &t->order,
+        for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done, &t->order, &t->phase,
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})
             b->release();
@@ -1162,6 +1171,17 @@ int klp_last_launch_info(klp_table* t, char* buf, size_t len) {
     return KLP_OK;
 }
 
+int klp_get_phase_times(klp_table* t, double* us9) {
+    if (!t || !us9) return fail(KLP_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(t->mu_);
+    DeviceGuard dg(t->device);
+    if (!dg.ok || !t->phase.p) return fail(KLP_ERR_ARG, "no phase stamps: set option phase_clock and evaluate first");
+    unsigned long long h[16];
+    KLP_CUDA(cudaMemcpy(h, t->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 9; ++k) us9[k] = h[k] ? (double)(h[k] - h[0]) * 1e-3 : -1.0;
+    return KLP_OK;
+}
+
 int klp_set_option(klp_table* t, const char* key, long value) {
     if (!t || !key) return fail(KLP_ERR_ARG, "null argument");
     std::lock_guard<std::recursive_mutex> lk(t->mu_);
@@ -1177,6 +1197,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "stage_mb") {
         if (value < 1 || value > 4096) return fail(KLP_ERR_ARG, "stage_mb");
         t->stage_mb = (int)value;
+    } else if (k == "phase_clock") {
+        t->phase_clock = value != 0;
     } else if (k == "coop") {
         t->use_coop = value != 0;
     } else if (k == "deposit_ring") {

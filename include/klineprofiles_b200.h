@@ -78,6 +78,11 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
  *  - the flat ".klpt" container written by lineprofiles_b200.tableio.save_table. */
 int klp_table_load(const char* path, int device, klp_table** out);
 
+/* A second handle on the SAME device copy of the frames with its own workspaces, streams and options: evaluations on the
+ * two handles may overlap (concurrent walkers / fit threads, one handle per thread or stream) without a second copy of the
+ * table.  The frames are freed when the last handle that references them is destroyed. */
+int klp_table_share(klp_table* t, klp_table** out);
+
 void klp_table_destroy(klp_table* t);
 
 /* dims[4] = {n_a, n_mu, n_r, n_g} */
@@ -112,11 +117,11 @@ int klp_eval_batch(klp_table* t, int model, int precision, long B, const double*
 
 /* Same, all pointers are device pointers on the table's device; work is enqueued on
  * `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised.
- * Concurrency: a table owns one set of device workspaces (fine-grid flux, deposit scratch,
- * per-call constants), so evaluations on ONE table must not overlap: klp_eval_batch and the XSPEC
- * symbols serialise themselves (a mutex per table), device-side calls must be ordered by the
- * caller (same stream, or events between streams).  Concurrent walkers use one table per stream --
- * the frames are shared read-only data, a second table costs a second copy of them. */
+ * Concurrency: a table handle owns one set of device workspaces (fine-grid flux, deposit scratch,
+ * per-call constants), so evaluations on ONE handle must not overlap: klp_eval_batch and the XSPEC
+ * symbols serialise themselves (a mutex per handle), device-side calls must be ordered by the
+ * caller (same stream, or events between streams).  Concurrent walkers use one handle per stream:
+ * klp_table_share gives further handles on the same device copy of the frames. */
 int klp_eval_batch_device(klp_table* t, int model, int precision, long B, const double* d_params,
                           const double* d_energy, int n_flux, const double* d_spectrum,
                           int spectrum_per_set, double* d_out, void* cuda_stream);

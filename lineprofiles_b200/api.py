@@ -47,6 +47,7 @@ def load_library():
     L.klp_model_nparams.argtypes = [C.c_int]
     L.klp_table_create.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_int, C.POINTER(vp)]
     L.klp_table_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.klp_table_share.argtypes = [vp, C.POINTER(vp)]
     L.klp_table_destroy.argtypes = [vp]
     L.klp_table_destroy.restype = None
     L.klp_table_dims.argtypes = [vp, C.POINTER(C.c_int)]
@@ -149,6 +150,12 @@ class Table:
         h = C.c_void_p()
         _check(load_library().klp_table_load(os.fsencode(path), int(device), C.byref(h)), "klp_table_load")
         return cls(h)
+
+    def share(self) -> "Table":
+        """Another handle on the same device frames with its own workspaces (for concurrent evaluations)."""
+        h = C.c_void_p()
+        _check(load_library().klp_table_share(self._h, C.byref(h)), "klp_table_share")
+        return Table(h)
 
     def close(self):
         if self._h:

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -115,8 +116,28 @@ struct EvalExtra {
 
 }  // namespace
 
+// The device copy of the frames, shared by a table and the workspaces cloned from it (klp_table_share).
+struct FrameStore {
+    int device = 0;
+    float* d_frames = nullptr;
+    float* d_spins = nullptr;
+    float* d_mus = nullptr;
+    unsigned char* d_frame_ok = nullptr;
+    ~FrameStore() {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        if (d_frames) cudaFree(d_frames);
+        if (d_spins) cudaFree(d_spins);
+        if (d_mus) cudaFree(d_mus);
+        if (d_frame_ok) cudaFree(d_frame_ok);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct klp_table {
     int device = 0;
+    std::shared_ptr<FrameStore> store;   // owner of d_frames / d_spins / d_mus / d_frame_ok once the table is complete
     int n_a = 0, n_mu = 0, n_r = 0, n_g = 0;
     size_t frame_stride = 0;
     std::vector<float> spins, mus;
@@ -757,7 +778,33 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     if (cudaMemcpy(t->d_spins, spins, sizeof(float) * n_a, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(t->d_mus, mus, sizeof(float) * n_mu, cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(KLP_ERR_CUDA, "cudaMemcpy(parameters)");
+    t->store = std::make_shared<FrameStore>();
+    t->store->device = device;
+    t->store->d_frames = t->d_frames;
+    t->store->d_spins = t->d_spins;
+    t->store->d_mus = t->d_mus;
+    t->store->d_frame_ok = t->d_frame_ok;
     *out = t;
+    return KLP_OK;
+}
+
+int klp_table_share(klp_table* t, klp_table** out) {
+    if (!out) return fail(KLP_ERR_ARG, "null out");
+    *out = nullptr;
+    if (!t) return fail(KLP_ERR_ARG, "null table");
+    if (t->device < 0 || !t->store) return fail(KLP_ERR_CUDA, "only device-resident tables can be shared (there is no CPU path)");
+    klp_table* w = new klp_table;
+    w->device = t->device;
+    w->store = t->store;
+    w->n_a = t->n_a; w->n_mu = t->n_mu; w->n_r = t->n_r; w->n_g = t->n_g;
+    w->frame_stride = t->frame_stride;
+    w->spins = t->spins;
+    w->mus = t->mus;
+    w->d_frames = t->d_frames; w->d_spins = t->d_spins; w->d_mus = t->d_mus; w->d_frame_ok = t->d_frame_ok;
+    w->frames_fast = t->frames_fast;
+    w->sm_count = t->sm_count; w->max_smem_optin = t->max_smem_optin; w->max_smem_sm = t->max_smem_sm;
+    w->coop_supported = t->coop_supported;
+    *out = w;
     return KLP_OK;
 }
 
@@ -969,10 +1016,14 @@ void klp_table_destroy(klp_table* t) {
     if (t->device >= 0) {
         DeviceGuard dg(t->device);
         cudaDeviceSynchronize();
-        if (t->d_frames) cudaFree(t->d_frames);
-        if (t->d_spins) cudaFree(t->d_spins);
-        if (t->d_mus) cudaFree(t->d_mus);
-        if (t->d_frame_ok) cudaFree(t->d_frame_ok);
+        if (t->store) {
+            t->store.reset();   // the frames go with the last table / workspace that references them
+        } else {                // (a table whose construction failed half way)
+            if (t->d_frames) cudaFree(t->d_frames);
+            if (t->d_spins) cudaFree(t->d_spins);
+            if (t->d_mus) cudaFree(t->d_mus);
+            if (t->d_frame_ok) cudaFree(t->d_frame_ok);
+        }
         for (Buf* b : {&t->cc32, &t->cc64, &t->fine, &t->prof, &t->conv_grid, &t->conv_avg, &t->scratch, &t->counter, &t->lims, &t->vals, &t->done, &t->order, &t->phase,
                        &t->d_energy, &t->d_spec, &t->d_params[0], &t->d_params[1], &t->d_out[0], &t->d_out[1],
                        &t->d_spec_slot[0], &t->d_spec_slot[1]})

@@ -588,3 +588,29 @@ def test_small_batch_cooperative_mode_is_bit_identical(gpu_table, oracle_table, 
         got = gpu_table.eval_batch("kline5", p, edges, precision=prec)
         want = oracle_table.eval_batch("kline5", p, edges, precision=prec)["out"]
         assert_parity(got, want, f"coop irregular {prec}")
+
+
+def test_shared_table_handles_evaluate_concurrently(gpu_table):
+    """klp_table_share: further handles on the same device frames, each with its own workspaces -- two host threads evaluate at
+    the same time (a sampler's walkers) and get what the single handle gives; the frames outlive the handle that loaded them."""
+    import threading
+    E = syn.energy_grid_linear(1000)
+    ps = [syn.random_params("kline5", 1500, seed=900 + k) for k in range(2)]
+    want = [gpu_table.eval_batch("kline5", p, E, precision="f32") for p in ps]
+    tab = klp.Table.from_arrays(syn.make_table(), 0)
+    handles = [tab.share(), tab.share()]
+    tab.close()                       # the clones keep the frames alive
+    got = [None, None]
+
+    def work(k):
+        for _ in range(3):
+            got[k] = handles[k].eval_batch("kline5", ps[k], E, precision="f32")
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(2):
+        assert np.array_equal(got[k], want[k])
+        handles[k].close()

@@ -56,6 +56,9 @@ const char* klp_last_error(void);
 /* Number of f64 parameters per set for a model (lmodel.dat), or -1. */
 int klp_model_nparams(int model);
 
+/* CUDA devices visible to this process (0 and KLP_ERR_CUDA when there is none: the library has no CPU path). */
+int klp_device_count(int* n);
+
 /* ---- transfer-function table (replaces reference io.readFitsFile, io.zig:53-87, and
  *      LineProfileTable.init, line-profile.zig:233-273) ------------------------------------ */
 

@@ -45,6 +45,7 @@ def load_library():
     dp, fp, zp, vp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.c_void_p
     L.klp_last_error.restype = C.c_char_p
     L.klp_model_nparams.argtypes = [C.c_int]
+    L.klp_device_count.argtypes = [C.POINTER(C.c_int)]
     L.klp_table_create.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_int, C.POINTER(vp)]
     L.klp_table_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.klp_table_share.argtypes = [vp, C.POINTER(vp)]

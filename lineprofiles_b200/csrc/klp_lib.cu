@@ -682,6 +682,14 @@ const char* klp_last_error(void) { return g_err.c_str(); }
 
 int klp_model_nparams(int model) { return model_nparams(model); }
 
+int klp_device_count(int* n) {
+    if (!n) return fail(KLP_ERR_ARG, "null argument");
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; return fail(KLP_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    return KLP_OK;
+}
+
 int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, int n_r, int n_g, const float* radii,
                      const float* gmin, const float* gmax, const float* upper, const float* lower, int device,
                      klp_table** out) {

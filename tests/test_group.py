@@ -140,3 +140,42 @@ def test_two_gpu_local_group(table_arrays, gpu_table):
     finally:
         g.close()
         t1.close()
+
+
+def _build_c_client(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(klp.api.library_path())
+    exe = tmp_path / "group_client"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                         os.path.join(root, "tests", "c", "group_client.c"), "-o", str(exe), "-L", libdir, "-lklineprofiles_b200",
+                         f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    return exe
+
+
+def test_c_group_client_builds_and_refuses_without_device(tmp_path, table_arrays):
+    """tests/c/group_client.c is the C99 view of the multi-GPU entry points; without a CUDA device it reports 'skipped' (77)."""
+    import subprocess
+    from lineprofiles_b200 import tableio
+    exe = _build_c_client(tmp_path)
+    tableio.save_table(str(tmp_path / "t.klpt"), syn.make_table(3, 4, 12, 30))
+    if _ndev() == 0:
+        run = subprocess.run([str(exe), str(tmp_path / "t.klpt"), "8"], capture_output=True, text=True)
+        assert run.returncode == 77, run.stdout + run.stderr
+
+
+@pytest.mark.gpu
+def test_c_group_client_drives_the_visible_gpus(tmp_path, table_arrays):
+    """The same C program on the GPU box: one table replica per GPU (two when present), klp_group_eval_batch == klp_eval_batch."""
+    import subprocess
+    from lineprofiles_b200 import tableio
+    exe = _build_c_client(tmp_path)
+    tableio.save_table(str(tmp_path / "t.klpt"), table_arrays)
+    run = subprocess.run([str(exe), str(tmp_path / "t.klpt"), "3001"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "group == single GPU: yes" in run.stdout
+    assert f"devices {min(_ndev(), 2)}" in run.stdout

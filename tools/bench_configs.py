@@ -163,34 +163,39 @@ def main():
               "cpu_oracle_f32_spectra_per_s": cpu, "cpu_cores": cores()})
 
     if 4 in cfgs:
-        # kconv10 MCMC-style batch of 1e6 walkers sharded over the ranks, one NCCL all-gather per chunk.
-        # On 1 GPU the 1/8 subset is run.
+        # kconv10 MCMC-style batch of 1e6 walkers sharded over the ranks through the C ABI's group entry
+        # (klp_group_eval_allgather_device): every GPU ends up with all spectra (32.8 GB at 1e6 x 4096 x f64); the NCCL gather
+        # of one chunk overlaps the kernels of the next.  On 1 GPU the 1/8 subset is run.
+        from lineprofiles_b200 import dist as kdist
         B = int(1000000 * args.scale) if WORLD > 1 else int(125000 * args.scale)
-        B = max(B, 1024 * WORLD)
-        lo, hi = shard_bounds(B, WORLD, RANK)
-        params = syn.random_params("kconv10", B)[lo:hi]
-        chunk = 16384
+        per = max(1024, B // WORLD)
+        B = per * WORLD
+        params = syn.random_params("kconv10", B)[RANK * per:(RANK + 1) * per]
         dp = torch.from_numpy(params).cuda()
-        out = torch.empty((chunk, 4096), dtype=torch.float64, device="cuda")
-        gathered = torch.empty((chunk * WORLD, 4096), dtype=torch.float64, device="cuda") if WORLD > 1 else None
-        checksum = torch.zeros((), dtype=torch.float64, device="cuda")
+        full = torch.empty((B, 4096), dtype=torch.float64, device="cuda")
+        group = kdist.rank_group(gt) if WORLD > 1 else klp.Group.local([gt])
+        st = torch.cuda.current_stream().cuda_stream
 
         def run():
-            n = hi - lo
-            per = -(-B // WORLD)
-            for c0 in range(0, per, chunk):   # every rank walks the same number of chunks
-                c1 = min(c0 + chunk, n)
-                if c1 > c0:
-                    device_eval(gt, "kconv10", dp[c0:c1], dE4k, 4096, out[: c1 - c0], spec=dspec, prec="f32")
-                if WORLD > 1:
-                    dist.all_gather_into_tensor(gathered, out)
+            group.eval_allgather_device("kconv10", [dp], [dE4k], 4096, [full], per, d_spectrum=[dspec], precision="f32", streams=[st])
         ms = timed(run, reps=1, warm=0 if B >= 100000 else 1)
+        ops = group.last_gather_ops()
         gt.set_option("conv_mode", 1)
         ms1 = timed(run, reps=1, warm=0)
         gt.set_option("conv_mode", 0)
-        emit({"config": 4, "what": f"kconv10, {B} walkers sharded x{WORLD}, 4096-bin grid, NCCL all-gather of the spectra per {chunk}-set chunk",
+        # every rank holds every spectrum: a checksum of checksums over the ranks must agree
+        chk = float(full.sum().item())
+        same = True
+        if WORLD > 1:
+            t = torch.tensor([chk, -chk], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            same = bool(t[0].item() == chk and -t[1].item() == chk)
+            same = bool(maxrank(0.0 if same else 1.0) == 0.0)
+        emit({"config": 4, "what": f"kconv10, {B} walkers sharded x{WORLD}, 4096-bin grid, klp_group_eval_allgather_device ({ops} grouped NCCL operations, each overlapping the next chunk's kernels)",
               "gpu": {"f32": {"spectra_per_s": B / (ms * 1e-3), "ms": ms}, "f32_conv_mode_1": {"spectra_per_s": B / (ms1 * 1e-3), "ms": ms1}},
-              "gathered_bytes_total": B * 4096 * 8 if WORLD > 1 else 0})
+              "gathered_bytes_total": B * 4096 * 8 if WORLD > 1 else 0, "all_ranks_hold_identical_spectra": same})
+        group.close()
+        del full
 
     if 5 in cfgs:
         # table resolution sweep: fused kline throughput + stand-alone blend kernel GB/s

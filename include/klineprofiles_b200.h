@@ -172,8 +172,8 @@ int klp_last_launch_info(klp_table* t, char* buf, size_t len);
 /* Diagnostics of the small-batch critical path (option "phase_clock" = 1): microseconds since the start of k_quad at which
  * the CTA holding the first work item passed 1 parameter unpacking, 2 radial grid + frame blend, 3 radial plan, 4 bin ranges,
  * 5 stage A (evaluate + deposit), 6 all CTAs of the set arrived, 7 ordered additions, 8 rebin (cooperative mode only for
- * 5 - 8); -1 where a stamp was not taken.  us9[0] is 0. */
-int klp_get_phase_times(klp_table* t, double* us9);
+ * 5 - 9), 9 the moment the last CTA of the set starts the rebin; -1 where a stamp was not taken.  us10[0] is 0. */
+int klp_get_phase_times(klp_table* t, double* us10);
 
 /* Self-test of the branch-free exact-arithmetic sequences (klp_kernels.cuh: div_by, div_gen, sqrt_gen)
  * against the IEEE intrinsics on n_total random + adversarial operands drawn from the ranges they are

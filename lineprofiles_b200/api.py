@@ -282,9 +282,9 @@ class Table:
 
     def phase_times(self):
         """Microseconds at which k_quad's first CTA passed its phase boundaries (option phase_clock = 1)."""
-        us = (C.c_double * 9)()
+        us = (C.c_double * 10)()
         _check(load_library().klp_get_phase_times(self._h, us), "klp_get_phase_times")
-        return dict(zip(("start", "unpack", "grid_blend", "plan", "bin_ranges", "stage_a", "all_arrived", "additions", "rebin"), (float(v) for v in us)))
+        return dict(zip(("start", "unpack", "grid_blend", "plan", "bin_ranges", "stage_a", "all_arrived", "additions", "rebin", "rebin_start"), (float(v) for v in us)))
 
     def arith_selftest(self, n_total: int, seed: int = 1):
         m = (C.c_ulonglong * 4)()

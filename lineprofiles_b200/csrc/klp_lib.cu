@@ -251,8 +251,6 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     splits = std::max(1, std::min(splits, kMaxSplits));
     q.splits = splits;
     q.coop = coop ? 1 : 0;
-    q.item_radii = coop ? 1 : kItemRadii;
-    q.item_subs = coop ? 4 : 1;
     const long long items = q.B * splits;
     const int grid = (int)std::min<long long>(items, resident);
     if (!FRAME_SMEM) {
@@ -441,8 +439,6 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
         q.rb = r;       // used by the cooperative small-batch mode, which rebins inside k_quad
         q.coop = 0;
-        q.item_radii = kItemRadii;
-        q.item_subs = 1;
         {
             NvtxRange nvtx_quad("klp integrate (k_quad)");
             TimedLaunch tl(t, st, 1);
@@ -1237,7 +1233,7 @@ int klp_get_phase_times(klp_table* t, double* us9) {
     if (!dg.ok || !t->phase.p) return fail(KLP_ERR_ARG, "no phase stamps: set option phase_clock and evaluate first");
     unsigned long long h[16];
     KLP_CUDA(cudaMemcpy(h, t->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 9; ++k) us9[k] = h[k] ? (double)(h[k] - h[0]) * 1e-3 : -1.0;
+    for (int k = 0; k < 10; ++k) us9[k] = h[k] ? (double)(h[k] - h[0]) * 1e-3 : -1.0;
     return KLP_OK;
 }
 

@@ -262,3 +262,19 @@ def test_xspec_static_archive_links_like_the_reference_package(tmp_path):
     # the smoke script skips cleanly where HEASoft is absent
     sm = subprocess.run([os.path.join(root, "tools", "xspec_smoke.sh")], capture_output=True, text=True)
     assert sm.returncode in (0, 77), sm.stdout + sm.stderr
+
+
+def test_hot_loop_fingerprint_is_the_measured_one():
+    """The schedule ptxas picks for the quadrature's hot loop moves the headline by up to 2.4 % when unrelated kernel code
+    changes (410.5 .. 420.1 ms per 50 000 sets for identical hot-loop source).  The fingerprint of the build that was measured
+    is recorded in profiles/hot_loop_fingerprint.json; a different one means: run tools/ab_lib.py on a B200 and record again."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "hot_loop_fingerprint.json")))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "hot_loop_fingerprint.py")], capture_output=True, text=True).stdout
+    assert json.loads(out) == rec["fingerprint"], "hot loop re-scheduled by ptxas: re-measure (tools/ab_lib.py) and run tools/hot_loop_fingerprint.py --write"

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Fingerprint of the quadrature's hot loop in a built library: SASS instruction count, `.reuse` operand flags, register
+moves.  Why: the loop is bound by the FP32 datapath / register-file bandwidth, and ptxas's register allocation and schedule
+for it change when UNRELATED code of the kernel changes -- round 2 measured 410.5 / 412.7 / 420.1 ms per 50 000 sets for three
+builds whose hot-loop source is identical (profiles/README.md, round 2).  A build whose fingerprint differs from the recorded
+one (profiles/hot_loop_fingerprint.json) has to be re-measured with tools/ab_lib.py before its throughput is quoted.
+
+usage: hot_loop_fingerprint.py [LIB] [--write]"""
+import json, os, re, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REC = os.path.join(ROOT, "profiles", "hot_loop_fingerprint.json")
+
+
+def fingerprint(lib, want="k_quadIfLi1024ELb1"):
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    cur, ins = None, []
+    for l in txt.splitlines():
+        m = re.search(r"Function : (\S+)", l)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and want in cur:
+            m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
+            if m:
+                ins.append((int(m.group(1), 16), m.group(2)))
+    for a, t in ins:
+        if "BRA" in t:
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) < a:
+                tgt = int(m.group(1), 16)
+                body = [x for x in ins if tgt <= x[0] <= a]
+                packed = sum(1 for x in body if re.search(r"F(FMA|MUL|ADD)2", x[1]))
+                if packed >= 90 and len(body) < 700:   # the first such loop is the pair-table path the benchmark runs
+                    return {"kernel": want, "instructions": len(body), "packed": packed, "reuse_flags": sum(t.count(".reuse") for _, t in body),
+                            "imad_mov": sum(1 for _, t in body if "IMAD.MOV" in t), "mov": sum(1 for _, t in body if t.startswith("MOV"))}
+    return None
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    lib = args[0] if args else os.path.join(ROOT, "lineprofiles_b200", "libklineprofiles_b200.so")
+    fp = fingerprint(lib)
+    print(json.dumps(fp))
+    if "--write" in sys.argv:
+        rec = json.load(open(REC)) if os.path.exists(REC) else {}
+        rec["fingerprint"] = fp
+        json.dump(rec, open(REC, "w"), indent=1)

@@ -302,6 +302,28 @@ def other_configs(klp, syn, gt, dev, peak_hbm, with_cpu=True, budget_s=25.0):
             res["config5"] = {"skipped": "time budget of the configs block spent"}
     except Exception as e:
         res["config5"] = {"error": repr(e)}
+    # ---- a table with zero-filled rows (the reference zero-fills radii a frame does not cover): only the sets that blend such a
+    #      frame leave the branch-free arithmetic; the rate of a random batch barely moves
+    try:
+        tz = syn.make_table()
+        n_mu = tz["n_mu"]
+        holes = [ia * n_mu + im for ia in (3, 11, 17, 24) for im in (2, 5, 11, 16)]
+        for f in holes:
+            tz["upper"][f, -6:] = 0.0     # the innermost radii of the frame: the ones the quadrature actually visits
+            tz["lower"][f, -6:] = 0.0
+        gz = klp.Table.from_arrays(tz, device=dev.index)
+        try:
+            Ez = syn.energy_grid_linear(1000)
+            Bz = 20000
+            dp, dE = torch.from_numpy(syn.random_params("kline5", Bz, seed=31)).to(dev), torch.from_numpy(Ez).to(dev)
+            rate_z, _, _ = device_rate(gz, "kline5", dp, dE, 1000, Bz, reps=2)
+            rate_0, _, _ = device_rate(gt, "kline5", dp, dE, 1000, Bz, reps=2)
+            res["table_with_zero_rows"] = {"frames_with_zero_rows": len(holes), "kline5_spectra_per_s": rate_z, "same_batch_on_the_clean_table": rate_0,
+                                           "launch": gz.last_launch_info()}
+        finally:
+            gz.close()
+    except Exception as e:
+        res["table_with_zero_rows"] = {"error": repr(e)}
     res["seconds"] = time.perf_counter() - t_start
     return res
 

@@ -156,8 +156,8 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
  * faster, equal to rounding), "coop" (1 = batches
  * much smaller than the GPU use one cooperative k_quad launch whose CTAs share a set's ordered additions and rebin it (default), 0 = separate
- * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring and add them
- * while evaluating: no DRAM traffic, ~4.5 % slower; default 0), "chunk" (sets per internal chunk), "stage_mb" (pinned staging per slot of the
+ * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring per CTA; a consumer warp adds them in order while the other warps evaluate:
+ * 0.15 GB of scratch instead of 1.8 GB and almost no DRAM traffic, but ~3.6x slower -- the ordered additions are 8 % of the instructions and one warp has 3 % of the issue slots; default 0), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the
  * host-buffer pipeline, default 128), "order" (1 = evaluate the costliest sets of a launch first (default), 0 = in input order), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */
@@ -212,8 +212,8 @@ int klp_group_eval_batch(klp_group* g, int model, int precision, long B, const d
 /* Device-resident buffers: member i (i < n_local) evaluates the B_local sets of d_params[i] -- rank r of
  * the group owns the global sets [r * B_local, (r+1) * B_local) -- and EVERY member ends up with all
  * nranks * B_local spectra in d_out_all[i], laid out [rank][set][bin].  The batch is processed in chunks
- * (options "gather_chunk", default 65535 sets = the kernel's launch cap, and "gather_tail", default 4096
- * sets for the final chunk): while chunk k+1 is integrated, the spectra of chunk k travel over NVLink on
+ * (options "gather_chunk", default 131072 sets, and "gather_tail", default 2048 sets for the final
+ * chunk): while chunk k+1 is integrated, the spectra of chunk k travel over NVLink on
  * a second, high-priority stream -- one grouped NCCL operation per chunk (a single ncclAllGather when the
  * batch is one chunk); only the short final chunk is gathered with nothing left to overlap.  Arrays have n_local entries; d_spectrum may be NULL for
  * kline / kline5; cuda_streams may be NULL (the group's own streams; see klp_group_synchronize).

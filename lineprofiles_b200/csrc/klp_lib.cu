@@ -174,7 +174,7 @@ struct klp_table {
     std::map<long long, int> quad_occ;   // (k_quad instantiation, shared memory) -> resident CTAs per SM
     bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
-    long chunk = 65535;
+    long chunk = 131072;        // sets per kernel launch (convolution models: at most 65535, the gridDim.y limit of their kernels)
     // timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -362,7 +362,7 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         if ((rc = t->conv_grid.ensure(sizeof(double) * 3 * kConvN))) return rc;  // grid | bin widths | reciprocals
         if ((rc = t->conv_avg.ensure(sizeof(double) * (size_t)n_flux))) return rc;
     }
-    const long long chunk = std::max<long long>(1, std::min<long long>(t->chunk, B));
+    const long long chunk = std::max<long long>(1, std::min<long long>(conv ? std::min<long>(t->chunk, 65535) : t->chunk, B));
     if ((rc = t->fine.ensure(sizeof(T) * (size_t)chunk * kFineG))) return rc;
     if (conv && (rc = t->prof.ensure(sizeof(double) * (size_t)chunk * (kConvN - 1)))) return rc;
 
@@ -1266,7 +1266,7 @@ int klp_set_option(klp_table* t, const char* key, long value) {
     } else if (k == "fast") {
         t->use_fast = value != 0;
     } else if (k == "chunk") {
-        if (value < 1 || value > 65535) return fail(KLP_ERR_ARG, "chunk");
+        if (value < 1 || value > (1 << 20)) return fail(KLP_ERR_ARG, "chunk");
         t->chunk = value;
     } else {
         return fail(KLP_ERR_ARG, "unknown option");

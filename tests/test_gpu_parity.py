@@ -217,9 +217,9 @@ def test_invariance_to_batching_knobs(gpu_table):
         for key, val in (("chunk", 97), ("splits", 5), ("quad_threads", 256), ("quad_threads", 512), ("quad_threads", 1024), ("splits", 63), ("splits", 300), ("frame_global", 1), ("deposit_ring", 1), ("order", 0)):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
-            gpu_table.set_option(key, {"chunk": 65535, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0, "order": 1}[key])
+            gpu_table.set_option(key, {"chunk": 131072, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0, "order": 1}[key])
     finally:
-        for key, val in (("chunk", 65535), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0), ("order", 1)):
+        for key, val in (("chunk", 131072), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0), ("order", 1)):
             gpu_table.set_option(key, val)
 
 

@@ -108,7 +108,7 @@ def test_two_gpu_local_group(table_arrays, gpu_table):
         Es = [torch.from_numpy(E).to(f"cuda:{d}") for d in (0, 1)]
         torch.cuda.synchronize(0)
         torch.cuda.synchronize(1)
-        for chunk, tail, n_ops in ((1000, 4096, 3), (65535, 4096, 1), (65535, 300, 2)):   # [1000, 1000, 500]; one all-gather; [2200, 300]
+        for chunk, tail, n_ops in ((1000, 4096, 3), (131072, 4096, 1), (131072, 300, 2)):   # [1000, 1000, 500]; one all-gather; [2200, 300]
             outs = [torch.zeros((2 * B, 1000), dtype=torch.float64, device=f"cuda:{d}") for d in (0, 1)]
             torch.cuda.synchronize(0)
             torch.cuda.synchronize(1)   # the group's own streams do not wait for torch's

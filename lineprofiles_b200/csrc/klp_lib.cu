@@ -286,7 +286,12 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         cfg.attrs = at;
         cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, k_quad<T, NT, FRAME_SMEM>, (const QuadArgs<T>)q);
-        if (e != cudaSuccess) return fail(KLP_ERR_CUDA, std::string("cooperative k_quad launch: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            // no co-residency guarantee to be had here (MPS limits, a debugger, ...): never again on this handle, separate kernels instead
+            cudaGetLastError();
+            t->coop_supported = false;
+            return launch_quad_impl<T, NT, FRAME_SMEM>(t, q, smem, fb, st);
+        }
     } else {
         k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
     }

@@ -36,6 +36,6 @@ out = {
                               "(FFMA2/FMUL2/FADD2 occupy the FP32 datapath for two cycles)",
     "gpu_time_ms_under_ncu": get("gpu__time_duration.sum") / (1e6 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0),
     "note": "DRAM traffic is the deposit scratch (evaluate-anywhere / add-in-order): 4 B written and read back per candidate (radius, bin); "
-            "the table itself stays in L2. Option deposit_ring keeps the deposits in L2 instead (-4.5 % throughput).",
+            "the table itself stays in L2. Option deposit_ring keeps them in an L2-resident ring with a consumer warp instead (no DRAM reads, 3.6x slower: DESIGN.md section 4).",
 }
 print(json.dumps(out, indent=1))

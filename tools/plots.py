@@ -34,7 +34,7 @@ def range_iterator(lo: float, hi: float, n: int) -> np.ndarray:
 
 def write_svg(path: str, x, y, title: str, w: int = 720, h: int = 360, pad: int = 45) -> None:
     x, y = np.asarray(x, float), np.nan_to_num(np.asarray(y, float))
-    x0, x1, y1 = x.min(), x.max(), max(y.max(), 1e-300)
+    x0, x1, y1 = x.min(), x.max(), max(float(y.max()), 1e-300)
     px = pad + (x - x0) / (x1 - x0) * (w - 2 * pad)
     py = h - pad - y / y1 * (h - 2 * pad)
     pts = " ".join(f"{a:.1f},{b:.1f}" for a, b in zip(px, py))
@@ -60,7 +60,9 @@ def main():
     try:
         jobs = []
         e = range_iterator(0.1, 12.0, 300)
-        jobs.append(("additive-example", e, klp.kline(e, [0.998, 70, 6.4, 3.0, 0.0, 50.0])))
+        jobs.append(("additive-example", e, klp.kline(e, [0.998, 70, 6.4, 3.0, 0.0, 50.0])))       # (the reference's vector, as it is)
+        klp.legacy_reset()
+        jobs.append(("additive-example-config1", e, klp.kline(e, syn.CONFIG1_PARAMS[0])))          # a = 0.998, 30 deg, ISCO..400, alpha = 3
         klp.legacy_reset()
         e = range_iterator(0.1, 12.0, 1000)
         jobs.append(("additive5-example", e, klp.kline5(e, [0.998, 80, 6.4, 1.0, 50.0, 3.0, 1.0, 2.0, 4.0, 5.0, 2.0, 0.0])))
@@ -74,7 +76,12 @@ def main():
         for name, e, y in jobs:
             np.savetxt(os.path.join(a.out, name + ".csv"), np.column_stack([e[:-1], y]), delimiter=",", header="energy_keV,flux")
             write_svg(os.path.join(a.out, name + ".svg"), e[:-1], y, name)
-            print(f"{name}: {y.size} bins, sum {np.nansum(y):.6g}, peak at {e[int(np.nanargmax(y))]:.3f} keV -> {a.out}/{name}.svg")
+            if np.all(np.isnan(y)):
+                # e.g. the reference's `additive-example` vector read with today's parameter order has rmax = 0: no radius is
+                # integrated, the normalisation divides by zero (Q10) -- the reference returns the same NaNs
+                print(f"{name}: {y.size} bins, ALL NaN (empty radial range -> sum 0 -> NaN, as in the reference) -> {a.out}/{name}.svg")
+            else:
+                print(f"{name}: {y.size} bins, sum {np.nansum(y):.6g}, peak at {e[int(np.nanargmax(y))]:.3f} keV -> {a.out}/{name}.svg")
     finally:
         klp.set_default_table(None)
         klp.legacy_reset()

@@ -107,11 +107,14 @@ std::recursive_mutex g_legacy_mu;
 klp_table* g_default_table = nullptr;  // installed by the caller (not owned)
 klp_table* g_owned_table = nullptr;    // lazily loaded singleton (xspec-wrapper.zig:61)
 
+constexpr long long kCtlDoneSets = 2048;   // per-set done flags that fit behind the work counters (see eval_device_t)
+
 struct EvalExtra {
     bool use_limits = false;
     double lim_lo = 0, lim_hi = 0;
     bool want_lims = false;  // write new end points of set 0 into table->d_lims
     bool setup_valid = false; // the per-call constants on the device are those of this very call (host pipeline): skip k_setup
+    void* lims_dst = nullptr; // device address for the new end points (default: the table's lims buffer)
 };
 
 }  // namespace
@@ -269,9 +272,13 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     q.vals = (T*)t->vals.p;
     q.done = nullptr;
     if (splits > 1) {
-        if ((rc = t->done.ensure(sizeof(unsigned) * 2 * (size_t)q.B))) return rc;
-        KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * 2 * (size_t)q.B, st));
-        q.done = (unsigned*)t->done.p;
+        if (q.done_prezeroed != nullptr && q.B <= kCtlDoneSets) {
+            q.done = q.done_prezeroed;   // single-launch call: zeroed together with the work counter (one memset instead of two)
+        } else {
+            if ((rc = t->done.ensure(sizeof(unsigned) * 2 * (size_t)q.B))) return rc;
+            KLP_CUDA(cudaMemsetAsync(t->done.p, 0, sizeof(unsigned) * 2 * (size_t)q.B, st));
+            q.done = (unsigned*)t->done.p;
+        }
     }
     if (coop) {
         q.rb.n_stage = (int)std::min<size_t>(fb / sizeof(double), 1u << 20);   // doubles of the dead frame area the fused rebin may use
@@ -361,7 +368,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
     Buf& ccb = sizeof(T) == 4 ? t->cc32 : t->cc64;
     int rc;
     if ((rc = ccb.ensure(sizeof(CallConsts<T>)))) return rc;
-    if ((rc = t->counter.ensure(sizeof(unsigned long long) * 4096))) return rc;
+    // work counters of up to 4096 launches, then (single-launch calls of at most kCtlDoneSets sets) the per-set done flags
+    if ((rc = t->counter.ensure(sizeof(unsigned long long) * 4096 + sizeof(unsigned) * 2 * kCtlDoneSets))) return rc;
     if ((rc = t->lims.ensure(sizeof(double) * 2))) return rc;
     if (conv) {
         if ((rc = t->conv_grid.ensure(sizeof(double) * 3 * kConvN))) return rc;  // grid | bin widths | reciprocals
@@ -387,7 +395,14 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
     }
     const long long n_chunks = (B + chunk - 1) / chunk;
     if (n_chunks > 4096) return fail(KLP_ERR_ARG, "batch too large for the chunk size");
-    KLP_CUDA(cudaMemsetAsync(t->counter.p, 0, sizeof(unsigned long long) * (size_t)n_chunks, st));
+    unsigned* done_pre = nullptr;
+    if (n_chunks == 1 && B <= kCtlDoneSets) {
+        // counter[0] and the done flags (placed right behind it for this purpose) in one memset
+        done_pre = reinterpret_cast<unsigned*>((unsigned long long*)t->counter.p + 1);
+        KLP_CUDA(cudaMemsetAsync(t->counter.p, 0, sizeof(unsigned long long) + sizeof(unsigned) * 2 * (size_t)B, st));
+    } else {
+        KLP_CUDA(cudaMemsetAsync(t->counter.p, 0, sizeof(unsigned long long) * (size_t)n_chunks, st));
+    }
     for (long long c = 0; c < n_chunks; ++c) {
         const long long off = c * chunk;
         const long long nb = std::min(chunk, B - off);
@@ -407,7 +422,8 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
         q.use_limits = ex.use_limits ? 1 : 0;
         q.lim_lo = (T)ex.lim_lo;
         q.lim_hi = (T)ex.lim_hi;
-        q.lims_out = (ex.want_lims && c == 0) ? (T*)t->lims.p : nullptr;
+        q.lims_out = (ex.want_lims && c == 0) ? (ex.lims_dst ? (T*)ex.lims_dst : (T*)t->lims.p) : nullptr;
+        q.done_prezeroed = done_pre;
         q.order = nullptr;
         q.phase_ns = nullptr;
         if (t->phase_clock) {
@@ -575,7 +591,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
     hc = std::max<long long>(16, std::min<long long>(hc, 65535));   // (very wide grids: fewer sets per slot, not more pinned memory)
     hc = std::min(hc, B);
-    const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux;
+    const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux + 16;   // (+16: the radial-grid end points of a legacy call ride behind the spectra)
     const size_t par_bytes = sizeof(double) * (size_t)hc * P;
     for (int k = 0; k < 2; ++k) {
         if ((rc = t->d_params[k].ensure(par_bytes)) || (rc = t->d_out[k].ensure(out_bytes)) ||
@@ -600,17 +616,19 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         }
         EvalExtra e2 = ex;
         e2.setup_valid = setup_cached;
+        const bool lims = lims_out && ex.want_lims;
+        const size_t out_len = sizeof(double) * (size_t)B * n_flux;
+        if (lims) e2.lims_dst = (char*)t->d_out[0].p + out_len;   // 16 spare bytes behind the spectra (see the buffer sizes above)
         rc = eval_device(t, model, precision, B, (const double*)t->d_params[0].p, (const double*)t->d_energy.p, n_flux, dspec, per_set,
                          (double*)t->d_out[0].p, s, e2);
         if (rc) return rc;
-        KLP_CUDA(cudaMemcpyAsync(t->h_out[0].p, t->d_out[0].p, sizeof(double) * (size_t)B * n_flux, cudaMemcpyDeviceToHost, s));
-        if (lims_out && ex.want_lims)
-            KLP_CUDA(cudaMemcpyAsync(t->h_lims.p, t->lims.p, precision == KLP_F32 ? sizeof(float) * 2 : sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+        KLP_CUDA(cudaMemcpyAsync(t->h_out[0].p, t->d_out[0].p, out_len + (lims ? 16 : 0), cudaMemcpyDeviceToHost, s));
         KLP_CUDA(cudaStreamSynchronize(s));
-        std::memcpy(out, t->h_out[0].p, sizeof(double) * (size_t)B * n_flux);
-        if (lims_out && ex.want_lims) {
-            if (precision == KLP_F32) { lims_out[0] = ((const float*)t->h_lims.p)[0]; lims_out[1] = ((const float*)t->h_lims.p)[1]; }
-            else { lims_out[0] = ((const double*)t->h_lims.p)[0]; lims_out[1] = ((const double*)t->h_lims.p)[1]; }
+        std::memcpy(out, t->h_out[0].p, out_len);
+        if (lims) {
+            const char* lp = (const char*)t->h_out[0].p + out_len;
+            if (precision == KLP_F32) { lims_out[0] = ((const float*)lp)[0]; lims_out[1] = ((const float*)lp)[1]; }
+            else { lims_out[0] = ((const double*)lp)[0]; lims_out[1] = ((const double*)lp)[1]; }
         }
         if (!setup_cached) {   // remember what the per-call constants on the device belong to
             t->setup_energy.assign(energy, energy + n_flux + 1);

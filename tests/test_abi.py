@@ -133,13 +133,27 @@ def test_lmodel_matches_library():
 
 
 def test_committed_ncu_figures_are_what_bench_reads():
-    """profiles/r01_quad_traffic.json (tools/ncu_traffic.py) carries the per-spectrum figures bench.py turns into
-    roofline.traffic, roofline_issue and roofline_fp32_pipe."""
+    """profiles/r*_quad_traffic.json (tools/ncu_traffic.py) carry the per-spectrum figures bench.py turns into roofline.traffic,
+    roofline_issue and roofline_fp32_pipe -- but only for the kernel instantiation the capture is of: bench.py compares the
+    capture's kernel name with klp_last_launch_info() and prints null + the reason on a mismatch (round 1 quoted a capture of
+    <float, 512, 0> for a <float, 1024, 1> run)."""
+    import importlib.util
     import json
-    d = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_quad_traffic.json")))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    newest = bench.latest_profile("r*_quad_traffic.json")
+    assert os.path.basename(newest) == "r02_quad_traffic.json"
+    d = json.load(open(newest))
     for key in ("sets_per_launch", "dram_bytes_read", "dram_bytes_write", "warp_instructions_per_set", "fma_pipe_cycles_per_set"):
         assert float(d[key]) > 0, key
-    assert d["sets_per_launch"] == 65535
+    shipped = "k_quad<float, 1024, 1> splits=1 ring=0 coop=0 fast_frames=600/600"
+    assert bench.kernel_matches(d["kernel"], shipped) and int(d.get("ring", 0)) == 0
+    old = json.load(open(os.path.join(root, "profiles", "r01_quad_traffic.json")))
+    assert not bench.kernel_matches(old["kernel"], shipped)            # the stale round-1 capture would be refused
+    assert not bench.kernel_matches(d["kernel"], "k_quad<double, 512, 1> splits=1 ring=0")
+    assert not bench.kernel_matches(d["kernel"], "")
 
 
 def test_c99_client_links_and_gets_the_xspec_error_convention(tmp_path):

@@ -72,7 +72,13 @@ def main():
         flux[150] = flux[200] = 1.0
         klp.kconv(e, [0.998, 40, 3.0, 0.0, 50.0], flux)
         tot = flux.sum()
-        jobs.append(("convolve-example", e, flux / tot if tot else flux))     # utils.normalize
+        jobs.append(("convolve-example", e, flux / tot if tot else flux))     # utils.normalize (the reference's vector: rmax = 0 -> empty)
+        klp.legacy_reset()
+        flux = np.zeros(299)
+        flux[150] = flux[200] = 1.0
+        klp.kconv(e, [0.998, 40, float(syn.r_isco(0.998)), 400.0, 3.0], flux)   # the same two delta lines, today's parameter order
+        tot = flux.sum()
+        jobs.append(("convolve-example-isco-400", e, flux / tot if tot else flux))
         for name, e, y in jobs:
             np.savetxt(os.path.join(a.out, name + ".csv"), np.column_stack([e[:-1], y]), delimiter=",", header="energy_keV,flux")
             write_svg(os.path.join(a.out, name + ".svg"), e[:-1], y, name)

@@ -24,6 +24,7 @@ def fingerprint(lib, want="k_quadIfLi1024ELb1"):
             m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
             if m:
                 ins.append((int(m.group(1), 16), m.group(2)))
+    found = []
     for a, t in ins:
         if "BRA" in t:
             m = re.search(r"0x([0-9a-f]+)", t)
@@ -31,9 +32,13 @@ def fingerprint(lib, want="k_quadIfLi1024ELb1"):
                 tgt = int(m.group(1), 16)
                 body = [x for x in ins if tgt <= x[0] <= a]
                 packed = sum(1 for x in body if re.search(r"F(FMA|MUL|ADD)2", x[1]))
-                if packed >= 90 and len(body) < 700:   # the first such loop is the pair-table path the benchmark runs
-                    return {"kernel": want, "instructions": len(body), "packed": packed, "reuse_flags": sum(t.count(".reuse") for _, t in body),
-                            "imad_mov": sum(1 for _, t in body if "IMAD.MOV" in t), "mov": sum(1 for _, t in body if t.startswith("MOV"))}
+                lds = sum(1 for _, t2 in body if t2.startswith("LDS"))
+                # the pair-table loops (one per stage-A mode: ring, cooperative, plain -- in that order in the kernel)
+                if packed == 102 and lds >= 20 and len(body) < 600 and tgt not in [f[0] for f in found]:
+                    found.append((tgt, {"kernel": want, "instructions": len(body), "packed": packed, "reuse_flags": sum(t2.count(".reuse") for _, t2 in body),
+                                        "imad_mov": sum(1 for _, t2 in body if "IMAD.MOV" in t2), "mov": sum(1 for _, t2 in body if t2.startswith("MOV"))}))
+    if found:
+        return found[-1][1]      # the plain mode (what the benchmark runs) is the last of them
     return None
 
 

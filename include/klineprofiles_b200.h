@@ -156,8 +156,8 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
  * faster, equal to rounding), "coop" (1 = batches
  * much smaller than the GPU use one cooperative k_quad launch whose CTAs share a set's ordered additions and rebin it (default), 0 = separate
- * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring per CTA; a consumer warp adds them in order while the other warps evaluate:
- * 0.15 GB of scratch instead of 1.8 GB and almost no DRAM traffic, but ~3.6x slower -- the ordered additions are 8 % of the instructions and one warp has 3 % of the issue slots; default 0), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the
+ * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring per CTA; four consumer warps add them in order, in registers, while the others evaluate:
+ * 0.15 GB of scratch instead of 1.8 GB and 6x less DRAM traffic, ~5 % slower; default 0; same results), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the
  * host-buffer pipeline, default 128), "order" (1 = evaluate the costliest sets of a launch first (default), 0 = in input order), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */

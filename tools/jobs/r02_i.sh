@@ -7,7 +7,7 @@ timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > $O/pytest.log 2>&1; echo "pytest exit $?" >> $O/pytest.log; tail -4 $O/pytest.log
 timeout 600 python bench.py --steps 5 --warmup 3 2> $O/bench.err | grep '^{' > $O/bench.json; echo "bench exit $?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> $O/bench.err | grep '^{' > $O/bench_reference.json; echo "reference arm exit $?"
-timeout 300 python tools/ab_lib.py build/libklp_14688b5.so lineprofiles_b200/libklineprofiles_b200.so > $O/ab.txt 2>&1; tail -2 $O/ab.txt
+timeout 300 python tools/ab_lib.py build/libklp_14688b5.so build/libklp_mode.so lineprofiles_b200/libklineprofiles_b200.so > $O/ab.txt 2>&1; tail -3 $O/ab.txt
 timeout 300 python tools/latency_breakdown.py > $O/latency_breakdown.txt 2>&1; grep "coop=1 B=    1\|exported" $O/latency_breakdown.txt
 timeout 200 python tools/plots.py --out $O/plots > $O/plots.txt 2>&1; cat $O/plots.txt
 timeout 300 python tools/fuzz.py 3 2048 > $O/fuzz.txt 2>&1; tail -4 $O/fuzz.txt

@@ -225,6 +225,8 @@ int klp_group_eval_allgather_device(klp_group* g, int model, int precision, long
 int klp_group_synchronize(klp_group* g);
 int klp_group_set_option(klp_group* g, const char* key, long value);
 int klp_group_last_gather_ops(const klp_group* g);   /* NCCL group operations issued by the last device-resident call */
+/* The chunk sizes the device-resident entry would use for B_local sets with the given options (sizes[cap]); returns their number. */
+int klp_group_chunk_plan(long B_local, long gather_chunk, long gather_tail, long* sizes, int cap);
 
 /* ---- the XSPEC model surface (reference xspec-wrapper.zig:425-530) -------------------------
  * void f(const double* energy   n_flux+1 bin edges,

@@ -85,6 +85,7 @@ def load_library():
     L.klp_group_synchronize.argtypes = [vp]
     L.klp_group_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.klp_group_last_gather_ops.argtypes = [vp]
+    L.klp_group_chunk_plan.argtypes = [C.c_long, C.c_long, C.c_long, C.POINTER(C.c_long), C.c_int]
     sig = [dp, C.c_int, dp, C.c_int, dp, dp, C.c_char_p]
     for name in MODELS:
         fn = getattr(L, name)
@@ -310,6 +311,15 @@ def nccl_version() -> int:
     v = C.c_int()
     _check(load_library().klp_nccl_version(C.byref(v)), "klp_nccl_version")
     return v.value
+
+
+def group_chunk_plan(B_local: int, gather_chunk: int = 131072, gather_tail: int = 2048):
+    """Chunk sizes of the device-resident multi-GPU entry for B_local sets per rank (few big chunks + a short tail)."""
+    buf = (C.c_long * 4096)()
+    n = load_library().klp_group_chunk_plan(int(B_local), int(gather_chunk), int(gather_tail), buf, 4096)
+    if n < 0:
+        raise KlpError("klp_group_chunk_plan: bad arguments")
+    return [int(buf[i]) for i in range(n)]
 
 
 def _vp_array(items):

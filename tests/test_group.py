@@ -29,6 +29,21 @@ def test_nccl_is_loaded_lazily_by_dlopen():
     assert len(klp.nccl_unique_id()) == 128
 
 
+def test_gather_chunk_plan():
+    """Few big chunks (every k_quad launch has an idle tail) and a short final chunk (its gather is the only one nothing overlaps);
+    small batches are one chunk = one ncclAllGather."""
+    from lineprofiles_b200.api import group_chunk_plan as plan
+    assert plan(100000) == [97952, 2048]
+    assert plan(100000, 65535, 4096) == [65535, 30369, 4096]
+    assert plan(1000000, 131072, 2048) == [131072] * 7 + [1000000 - 7 * 131072 - 2048, 2048]
+    assert plan(3000) == [3000] and plan(1024) == [1024] and plan(4096) == [4096]      # B <= 2 * tail: no tail chunk
+    assert plan(5000, 1000, 0) == [1000] * 5
+    assert plan(2500, 131072, 300) == [2200, 300]
+    assert plan(0) == []
+    for B in (1, 17, 4097, 65536, 123457):
+        assert sum(plan(B)) == B and all(c > 0 for c in plan(B))
+
+
 def _ndev():
     import torch
     return torch.cuda.device_count() if torch.cuda.is_available() else 0

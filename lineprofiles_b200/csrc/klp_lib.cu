@@ -457,7 +457,9 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
             r.out_stride = (size_t)n_flux;
         }
         r.caller_edges = conv ? 0 : 1;
-        r.n_stage = r.n_out <= 4096 ? 4096 : 0;   // 32 KB of dynamic shared memory for the per-bin values
+        // per-bin values staged in dynamic shared memory, sized to the grid (1000 bins: 8 + 16 KB per CTA, 9 CTAs per SM;
+        // the fixed 32 KB of earlier builds allowed 4, and the sequential in-order total of a set hides behind other sets only)
+        r.n_stage = r.n_out <= 4096 ? ((r.n_out + 1) & ~1) : 0;
         q.rb = r;       // used by the cooperative small-batch mode, which rebins inside k_quad
         q.coop = 0;
         {

@@ -154,7 +154,8 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
 /* Tuning knobs (testing / benchmarking): "quad_threads" (256, 512 or 1024; 0 = default: 1024 in f32, 512 in f64), "splits" (CTAs
  * that share one set, 0 = auto: more than one only when the batch is smaller than the GPU), "conv_mode" (0 = the
  * reference's operation order in the convolution, bit-exact (default); 1 = cumulative-profile formulation, ~4x
- * faster, equal to rounding), "coop" (1 = batches
+ * faster, equal to rounding), "conv_src_smem" (conv_mode 1 on grids of at most 4096 bins: 1 = the per-source pairs {2/(x_i+x_i+1), spectrum_i}
+ * are staged in shared memory next to the cumulative table (default; 20 % faster), 0 = they are read through L1; equal to rounding), "coop" (1 = batches
  * much smaller than the GPU use one cooperative k_quad launch whose CTAs share a set's ordered additions and rebin it (default), 0 = separate
  * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring per CTA; four consumer warps add them in order, in registers, while the others evaluate:
  * 0.15 GB of scratch instead of 1.8 GB and 6x less DRAM traffic, ~5 % slower; default 0; same results), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the

@@ -166,6 +166,7 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    int conv_src_smem = 1; // conv_mode 1: stage the per-source {avg, spectrum} pairs in shared memory (512-thread CTAs; grids up to 4096 bins)
     bool use_order = true;      // evaluate the costliest sets of a launch first
     // the per-call constants currently on the device (host pipeline only): energy grid, precision, conv
     std::vector<double> setup_energy;
@@ -500,8 +501,15 @@ int eval_device_t(klp_table* t, int model, long long B, const double* d_params, 
                 constexpr int EPL = 2;
                 const int chunks = (n_flux + 32 * EPL - 2) / (32 * EPL - 1);
                 const unsigned cps = (unsigned)std::max<long long>(1, std::min<long long>((chunks + 7) / 8, fill));
-                KLP_CUDA(cudaFuncSetAttribute(k_conv_cum<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvFastSmemBytes));
-                k_conv_cum<EPL><<<dim3(cps, (unsigned)nb), 256, kConvFastSmemBytes, st>>>(ca);
+                if (t->conv_src_smem && n_flux <= 4096) {   // {avg, spectrum} pairs staged in shared memory too
+                    const size_t smem = kConvCumSrcOffset + sizeof(double2) * (size_t)n_flux;
+                    const unsigned cps2 = (unsigned)std::max<long long>(1, std::min<long long>((chunks + 15) / 16, fill));
+                    KLP_CUDA(cudaFuncSetAttribute(k_conv_cum<EPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kConvCumSrcOffset + sizeof(double2) * 4096)));
+                    k_conv_cum<EPL, true><<<dim3(cps2, (unsigned)nb), 512, smem, st>>>(ca);
+                } else {
+                    KLP_CUDA(cudaFuncSetAttribute(k_conv_cum<EPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvFastSmemBytes));
+                    k_conv_cum<EPL, false><<<dim3(cps, (unsigned)nb), 256, kConvFastSmemBytes, st>>>(ca);
+                }
             } else if (t->conv_mode == 0) {   // the reference's operation order (default)
                 const unsigned cps = (unsigned)std::max<long long>(1, std::min<long long>((n_flux + kConvXThreads - 1) / kConvXThreads, fill));
                 KLP_CUDA(cudaFuncSetAttribute(k_conv_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvXSmemBytes));
@@ -1285,6 +1293,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
         t->deposit_ring = value != 0;
     } else if (k == "frame_global") {
         t->frame_global = value != 0;
+    } else if (k == "conv_src_smem") {
+        t->conv_src_smem = value ? 1 : 0;
     } else if (k == "conv_mode") {
         if (value < 0 || value > 3) return fail(KLP_ERR_ARG, "conv_mode");
         t->conv_mode = (int)value;

@@ -354,15 +354,20 @@ def test_conv_mode_cumulative_profile(gpu_table, oracle_table):
                 gpu_table.set_option("conv_mode", 0)
                 exact = gpu_table.eval_batch(model, p, E, spectrum=sp, precision="f32")
                 gpu_table.set_option("conv_mode", 1)
-                fast = gpu_table.eval_batch(model, p, E, spectrum=sp, precision="f32")
                 scale = np.max(np.abs(exact), axis=-1, keepdims=True)
-                err = np.abs(fast - exact) / (np.abs(exact) + 1e-3 * scale)
-                assert np.max(err) < 1e-9, (model, n, float(np.max(err)))
+                # both variants of the kernel: per-source {avg, spectrum} pairs staged in shared memory (default) or read from L1
+                for src_smem in (1, 0):
+                    gpu_table.set_option("conv_src_smem", src_smem)
+                    fast = gpu_table.eval_batch(model, p, E, spectrum=sp, precision="f32")
+                    err = np.abs(fast - exact) / (np.abs(exact) + 1e-3 * scale)
+                    assert np.max(err) < 1e-9, (model, n, src_smem, float(np.max(err)))
+                gpu_table.set_option("conv_src_smem", 1)
             want = oracle_table.eval_batch(model, p, E, spectrum=spec, precision="f32", threads=4)["out"]
             gpu_table.set_option("conv_mode", 1)
             assert_parity(gpu_table.eval_batch(model, p, E, spectrum=spec, precision="f32"), want, f"conv_mode 1 {model} n={n}")
     finally:
         gpu_table.set_option("conv_mode", 0)
+        gpu_table.set_option("conv_src_smem", 1)
 
 
 def test_fits_table_evaluates_like_arrays(tmp_path, gpu_table, table_arrays):

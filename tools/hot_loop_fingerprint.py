@@ -34,7 +34,7 @@ def fingerprint(lib, want="k_quadIfLi1024ELb1"):
                 packed = sum(1 for x in body if re.search(r"F(FMA|MUL|ADD)2", x[1]))
                 lds = sum(1 for _, t2 in body if t2.startswith("LDS"))
                 # the pair-table loops (one per stage-A mode: ring, cooperative, plain -- in that order in the kernel)
-                if packed in (90, 102) and lds >= 20 and len(body) < 600 and tgt not in [f[0] for f in found]:
+                if 80 <= packed <= 102 and lds >= 20 and len(body) < 600 and tgt not in [f[0] for f in found]:
                     found.append((tgt, {"kernel": want, "instructions": len(body), "packed": packed, "reuse_flags": sum(t2.count(".reuse") for _, t2 in body),
                                         "imad_mov": sum(1 for _, t2 in body if "IMAD.MOV" in t2), "mov": sum(1 for _, t2 in body if t2.startswith("MOV"))}))
     if found:

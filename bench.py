@@ -175,6 +175,12 @@ def cpu_baseline_conv(syn, params, energy, spec, n_sets: int = 4):
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{n} kconv sets of the same workload in {dt:.1f} s"}, st["conv_pairs"] / n
 
 
+def recorded_fingerprint():
+    """Hot-loop fingerprint of the build whose measurements are committed (tests/test_abi.py checks that the built library has it)."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "hot_loop_fingerprint.json")
+    return json.load(open(p)).get("fingerprint") if os.path.exists(p) else None
+
+
 def latest_profile(name_glob: str):
     import glob
     c = sorted(glob.glob(os.path.join(ROOT, "profiles", name_glob)))
@@ -501,11 +507,17 @@ def main():
         tp = latest_profile("r*_quad_traffic.json")
         if tp and prec == "f32":
             tj = json.load(open(tp))
-            if kernel_matches(tj.get("kernel", ""), launch_info) and int(tj.get("ring", 0)) == int("ring=1" in launch_info):
-                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * sets_per_launch / tj["sets_per_launch"]
-            else:
+            fp_now = recorded_fingerprint()
+            if not (kernel_matches(tj.get("kernel", ""), launch_info) and int(tj.get("ring", 0)) == int("ring=1" in launch_info)):
                 stale = f"{os.path.basename(tp)} is a capture of '{tj.get('kernel')}' but this run launched '{launch_info}'"
                 tj = None
+            elif tj.get("hot_loop_fingerprint") != fp_now:
+                # same instantiation, different hot loop (e.g. captured before an arithmetic change): instruction counts differ
+                stale = (f"{os.path.basename(tp)} was captured from a build whose hot loop is {tj.get('hot_loop_fingerprint')}, "
+                         f"the measured build's is {fp_now} (profiles/hot_loop_fingerprint.json)")
+                tj = None
+            else:
+                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * sets_per_launch / tj["sets_per_launch"]
         roofline = {"bound": "hbm", "kernel": launch_info, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_spectrum": bytes_per_set, "avg_launch_ms": avg_launch_ms,

@@ -166,12 +166,13 @@ struct klp_table {
     bool use_fast = true;  // option "fast"
     int splits = 0;        // 0 = auto
     int conv_mode = 0;     // 0 = the reference's operation order (bit-exact), 1 = cumulative-profile formulation
+    int stage_tail = 4096; // sets of the final staging chunk of the host-buffer pipeline (its copy-out overlaps nothing)
     int conv_src_smem = 1; // conv_mode 1: stage the per-source {avg, spectrum} pairs in shared memory (512-thread CTAs; grids up to 4096 bins)
     bool use_order = true;      // evaluate the costliest sets of a launch first
     // the per-call constants currently on the device (host pipeline only): energy grid, precision, conv
     std::vector<double> setup_energy;
     int setup_precision = -1, setup_conv = -1;
-    int stage_mb = 128;         // pinned staging per slot of the host pipeline (MB of output)
+    int stage_mb = 256;         // pinned staging per slot of the host pipeline (MB of output)
     bool use_coop = true;       // option "coop": cooperative small-batch mode of k_quad (fused rebin) when the batch is tiny
     bool coop_supported = false;
     bool rebin_attr_set[2] = {false, false};
@@ -596,7 +597,7 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     }
     // (no synchronisation needed here: copies from pageable memory are staged before cudaMemcpyAsync returns, and the kernels
     // that read the grid / spectrum are enqueued on the same stream)
-    // staging chunk: t->stage_mb of output per slot (two slots; default 128 MB).  Larger chunks amortise the idle tail of
+    // staging chunk: t->stage_mb of output per slot (two slots; default 256 MB).  Larger chunks amortise the idle tail of
     // every k_quad launch, smaller ones shorten the last, un-overlapped copy-out.
     long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
     hc = std::max<long long>(16, std::min<long long>(hc, 65535));   // (very wide grids: fewer sets per slot, not more pinned memory)
@@ -610,7 +611,19 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         if (conv && per_set)
             if ((rc = t->d_spec_slot[k].ensure(out_bytes)) || (rc = t->h_spec_slot[k].ensure(out_bytes))) return rc;
     }
-    const long long n_chunks = (B + hc - 1) / hc;
+    // Chunk sizes: full slots, then a SHORT final chunk.  The copy-out of the last chunk (D2H + the copy from the pinned slot
+    // into the caller's buffer: ~15 ms for a 128 MB slot) overlaps nothing, so the last chunk is cut to stage_tail sets
+    // (default 4096: ~4 ms exposed, and its ~30 ms of kernels cover the copy-out of the chunk before it; measured on 1e5 kline5 sets: 128 MB slots 133.0 k spectra/s, 256 MB slots without the short chunk 127.9 k, with it 134.5 k).
+    std::vector<long long> cuts;
+    {
+        long long tail = std::min<long long>(t->stage_tail, hc / 4);
+        if (tail < 1 || B <= hc + tail) tail = 0;
+        long long off = 0;
+        const long long body = B - tail;
+        while (off < body) { const long long nb = std::min(hc, body - off); cuts.push_back(nb); off += nb; }
+        if (tail > 0) cuts.push_back(tail);
+    }
+    const long long n_chunks = (long long)cuts.size();
     if ((rc = t->h_lims.ensure(16))) return rc;
     if (n_chunks == 1) {
         // One staging chunk (the XSPEC call pattern is B = 1): everything on ONE stream, one synchronisation -- no events, no
@@ -655,9 +668,10 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
         pending_off[k] = -1;
         return KLP_OK;
     };
-    for (long long c = 0; c < n_chunks; ++c) {
+    long long off = 0;
+    for (long long c = 0; c < n_chunks; off += cuts[(size_t)c], ++c) {
         const int k = (int)(c & 1);
-        const long long off = c * hc, nb = std::min(hc, B - off);
+        const long long nb = cuts[(size_t)c];
         if ((rc = drain(k))) return rc;
         std::memcpy(t->h_params[k].p, params + (size_t)off * P, sizeof(double) * (size_t)nb * P);
         KLP_CUDA(cudaMemcpyAsync(t->d_params[k].p, t->h_params[k].p, sizeof(double) * (size_t)nb * P, cudaMemcpyHostToDevice, t->s_h2d));
@@ -1293,6 +1307,9 @@ int klp_set_option(klp_table* t, const char* key, long value) {
         t->deposit_ring = value != 0;
     } else if (k == "frame_global") {
         t->frame_global = value != 0;
+    } else if (k == "stage_tail") {
+        if (value < 0 || value > 65535) return fail(KLP_ERR_ARG, "stage_tail");
+        t->stage_tail = (int)value;
     } else if (k == "conv_src_smem") {
         t->conv_src_smem = value ? 1 : 0;
     } else if (k == "conv_mode") {

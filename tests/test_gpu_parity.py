@@ -508,10 +508,15 @@ def test_host_pipeline_multiple_staging_chunks(gpu_table):
     one_c = gpu_table.eval_batch("kconv", pc, E2, spectrum=spec, precision="f32")
     gpu_table.set_option("stage_mb", 1)
     try:
-        assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), one)        # 131 sets per slot: 6 chunks
+        # 131 sets per slot: five full chunks + 13 sets + the short final chunk (stage_tail, capped at a quarter slot: 32 sets)
+        assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), one)
         assert np.array_equal(gpu_table.eval_batch("kconv", pc, E2, spectrum=spec, precision="f32"), one_c)
+        for tail in (0, 1, 7):   # equal chunks; one-set and ragged final chunks
+            gpu_table.set_option("stage_tail", tail)
+            assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), one), tail
     finally:
-        gpu_table.set_option("stage_mb", 128)
+        gpu_table.set_option("stage_mb", 256)
+        gpu_table.set_option("stage_tail", 4096)
 
 
 def test_installed_table_closed_then_xspec_symbol_zero_fills(table_arrays, capfd):

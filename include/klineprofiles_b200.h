@@ -158,7 +158,8 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * are staged in shared memory next to the cumulative table (default; 20 % faster), 0 = they are read through L1; equal to rounding), "coop" (1 = batches
  * much smaller than the GPU use one cooperative k_quad launch whose CTAs share a set's ordered additions and rebin it (default), 0 = separate
  * kernels; same results), "deposit_ring" (1 = keep the quadrature's deposits in an L2-resident ring per CTA; four consumer warps add them in order, in registers, while the others evaluate:
- * 0.15 GB of scratch instead of 1.8 GB and 6x less DRAM traffic, ~5 % slower; default 0; same results), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the
+ * 0.15 GB of scratch instead of 1.8 GB and 6x less DRAM traffic, ~5 % slower; default 0; same results), "ring_discard" (deposit ring only: 1 = a consumer discards the 128-byte lines it has added from the L2 (discard.global.L2) so that dead
+ * deposits are never written back to DRAM (default), 0 = leave them to the L2's write-back; same results), "chunk" (sets per kernel launch, default 131072; convolution models at most 65535), "stage_mb" (pinned staging per slot of the
  * host-buffer pipeline, default 256), "stage_tail" (sets of that pipeline's final chunk, whose copy-out nothing overlaps; default 4096, 0 = equal chunks), "order" (1 = evaluate the costliest sets of a launch first (default), 0 = in input order), "fast" (1 = allow the branch-free exact-arithmetic
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */

@@ -178,6 +178,7 @@ struct klp_table {
     bool rebin_attr_set[2] = {false, false};
     std::map<long long, int> quad_occ;   // (k_quad instantiation, shared memory) -> resident CTAs per SM
     bool deposit_ring = false;  // L2 ring of deposits + concurrent ordered additions (no DRAM traffic, -4.5 % throughput)
+    bool ring_discard = true;   // deposit ring: consumed lines are discarded from the L2 (discard.global.L2) instead of written back
     bool frame_global = false;  // keep the blended frame in the per-CTA global scratch even when it fits shared memory
     long chunk = 131072;        // sets per kernel launch (convolution models: at most 65535, the gridDim.y limit of their kernels)
     // timing
@@ -265,8 +266,8 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
     }
     // deposit scratch: a ring of kRingRadii radii per CTA when every set is owned by one CTA (it stays in L2), the whole
     // (radius, bin) plane per set when sets are shared by several CTAs (small batches)
-    q.ring_mode = t->deposit_ring ? 1 : 0;
-    q.vals_stride = (size_t)((splits > 1 || !q.ring_mode) ? kRadial : kRingRadii) * kFineG;   // dense (radius, bin) addressing
+    q.ring_mode = t->deposit_ring ? (t->ring_discard ? 2 : 1) : 0;
+    q.vals_stride = (splits > 1 || !q.ring_mode) ? (size_t)kRadial * kFineG : (size_t)kRingRadii * kRingStride;   // dense (radius, bin) addressing
     const size_t regions = splits > 1 ? (size_t)std::min<long long>(q.B, kSplitRegions) : (size_t)grid;
     q.regions = (long long)regions;
     int rc = t->vals.ensure(regions * q.vals_stride * sizeof(T));
@@ -305,8 +306,8 @@ template <class T, int NT, bool FRAME_SMEM> int launch_quad_impl(klp_table* t, Q
         k_quad<T, NT, FRAME_SMEM><<<grid, NT, smem, st>>>(q);
     }
     KLP_CUDA(cudaGetLastError());
-    std::snprintf(t->quad_variant, sizeof(t->quad_variant), "k_quad<%s, %d, %d> splits=%d ring=%d coop=%d", sizeof(T) == 4 ? "float" : "double", NT,
-                  FRAME_SMEM ? 1 : 0, splits, q.ring_mode, q.coop);
+    std::snprintf(t->quad_variant, sizeof(t->quad_variant), "k_quad<%s, %d, %d> splits=%d ring=%d%s coop=%d", sizeof(T) == 4 ? "float" : "double", NT,
+                  FRAME_SMEM ? 1 : 0, splits, q.ring_mode ? 1 : 0, q.ring_mode == 2 ? " discard=1" : "", q.coop);
     return KLP_OK;
 }
 
@@ -1305,6 +1306,8 @@ int klp_set_option(klp_table* t, const char* key, long value) {
         t->use_coop = value != 0;
     } else if (k == "deposit_ring") {
         t->deposit_ring = value != 0;
+    } else if (k == "ring_discard") {
+        t->ring_discard = value != 0;
     } else if (k == "frame_global") {
         t->frame_global = value != 0;
     } else if (k == "stage_tail") {

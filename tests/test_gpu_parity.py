@@ -218,8 +218,20 @@ def test_invariance_to_batching_knobs(gpu_table):
             gpu_table.set_option(key, val)
             assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), (key, val)
             gpu_table.set_option(key, {"chunk": 131072, "splits": 0, "quad_threads": 0, "frame_global": 0, "deposit_ring": 0, "order": 1}[key])
+        # the deposit ring with and without discarding the consumed lines from the L2 (a discarded line that is reused must
+        # never be read before it is rewritten: repeat, in both precisions, with 256- and 1024-thread CTAs)
+        base64 = gpu_table.eval_batch("kline5", p, E, precision="f64")
+        gpu_table.set_option("deposit_ring", 1)
+        for disc in (1, 0, 1):
+            gpu_table.set_option("ring_discard", disc)
+            for nt in (0, 256):
+                gpu_table.set_option("quad_threads", nt)
+                assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f32"), base), ("ring_discard", disc, nt)
+                assert ("discard=1" in gpu_table.last_launch_info()) == bool(disc)
+            gpu_table.set_option("quad_threads", 0)
+            assert np.array_equal(gpu_table.eval_batch("kline5", p, E, precision="f64"), base64), ("ring_discard f64", disc)
     finally:
-        for key, val in (("chunk", 131072), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0), ("order", 1)):
+        for key, val in (("chunk", 131072), ("splits", 0), ("quad_threads", 0), ("frame_global", 0), ("deposit_ring", 0), ("order", 1), ("ring_discard", 1)):
             gpu_table.set_option(key, val)
 
 

@@ -260,7 +260,7 @@ def other_configs(klp, syn, gt, dev, peak_hbm, with_cpu=True, budget_s=25.0):
                 gt.set_option("conv_mode", 0)
             ach = 8.0 * pairs * B3 / (tm["conv"] * 1e-3) / 1e9 if (pairs and tm["conv"] > 0) else None
             r3[name] = {"spectra_per_s": rate, "ms_per_batch": ms, "k_quad_ms": tm["quad"], "k_conv_ms": tm["conv"], "k_rebin_ms": tm["rebin"],
-                        "roofline": {"bound": "fp64_cuda_core", "kernel": "k_conv_cum<2>" if mode else "k_conv_exact", "achieved": ach, "peak": pk64,
+                        "roofline": {"bound": "fp64_cuda_core", "kernel": "k_conv_cum<2, true>" if mode else "k_conv_exact", "achieved": ach, "peak": pk64,
                                      "unit": "GFLOP/s", "frac": ach / pk64 if ach and pk64 else None,
                                      "flops": "8 x in-window (source, output) pairs (SURVEY.md 8d A_F,conv); pairs/set counted by the oracle: %s" % ("%.4g" % pairs if pairs else "n/a"),
                                      "peak_source": "klp_fma_peak_gflops f64 (DFMA microbenchmark on this GPU)"}}

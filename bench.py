@@ -308,8 +308,8 @@ def other_configs(klp, syn, gt, dev, peak_hbm, with_cpu=True, budget_s=25.0):
             res["config5"] = {"skipped": "time budget of the configs block spent"}
     except Exception as e:
         res["config5"] = {"error": repr(e)}
-    # ---- a table with zero-filled rows (the reference zero-fills radii a frame does not cover): only the sets that blend such a
-    #      frame leave the branch-free arithmetic; the rate of a random batch barely moves
+    # ---- a table with zero-filled rows (the reference zero-fills radii a frame does not cover): exact zeros stay inside the
+    #      branch-free arithmetic (checked per set on the blended frame)
     try:
         tz = syn.make_table()
         n_mu = tz["n_mu"]

@@ -789,16 +789,17 @@ int klp_table_create(const float* spins, int n_a, const float* mus, int n_mu, in
     if (cudaMalloc(&t->d_spins, sizeof(float) * n_a) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(spins)");
     if (cudaMalloc(&t->d_mus, sizeof(float) * n_mu) != cudaSuccess) return bail(KLP_ERR_NOMEM, "cudaMalloc(mus)");
     {
-        // operand-range precondition of the FAST arithmetic, per frame: branches in [2^-20, 2^20], g limits in [2^-10, 2^10].
-        // A set may use the FAST sequences when its four frames pass (the reference zero-fills missing radii: one such
-        // frame must not slow down the whole table).
+        // operand-range precondition of the FAST arithmetic, per frame: branches exactly 0 or in [2^-20, 2^20] (the reference
+        // zero-fills radii a frame does not cover; a zero numerator is exact in every FAST sequence, and what blending a zero
+        // with its neighbours produces is checked per set on the blended frame, k_quad phase 1), g limits in [2^-10, 2^10].
+        // A set may use the FAST sequences when its four frames pass.
         std::vector<unsigned char> okv(F, 1);
         for (size_t f = 0; f < F; ++f) {
             bool ok = true;
             const float* u = upper + f * (size_t)n_r * n_g;
             const float* l = lower + f * (size_t)n_r * n_g;
             for (size_t i = 0; i < (size_t)n_r * n_g && ok; ++i)
-                ok = u[i] >= 9.5367431640625e-07f && u[i] <= 1048576.f && l[i] >= 9.5367431640625e-07f && l[i] <= 1048576.f;
+                ok = (u[i] == 0.f || (u[i] >= 9.5367431640625e-07f && u[i] <= 1048576.f)) && (l[i] == 0.f || (l[i] >= 9.5367431640625e-07f && l[i] <= 1048576.f));
             const float* gn = gmin + f * n_r;
             const float* gx = gmax + f * n_r;
             for (int i = 0; i < n_r && ok; ++i)

@@ -153,8 +153,9 @@ def test_committed_ncu_figures_are_what_bench_reads():
     # ... and only for the very hot loop the capture was taken from: the one-correction division changed the instruction
     # counts of the same instantiation, so the capture carries the fingerprint of its build
     assert d["hot_loop_fingerprint"] == bench.recorded_fingerprint()
-    stale = json.load(open(os.path.join(root, "profiles", "r02_quad_two_corrections_traffic_capture.json")))
-    assert stale.get("hot_loop_fingerprint") != bench.recorded_fingerprint()
+    for superseded in ("r02_quad_two_corrections_traffic_capture.json", "r02_quad_493_instruction_loop_capture.json"):
+        stale = json.load(open(os.path.join(root, "profiles", superseded)))
+        assert stale.get("hot_loop_fingerprint") != bench.recorded_fingerprint()
     old = json.load(open(os.path.join(root, "profiles", "r01_quad_traffic.json")))
     assert not bench.kernel_matches(old["kernel"], shipped)            # the stale round-1 capture would be refused
     assert not bench.kernel_matches(d["kernel"], "k_quad<double, 512, 1> splits=1 ring=0")

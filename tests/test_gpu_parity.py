@@ -557,9 +557,10 @@ def test_installed_table_closed_then_xspec_symbol_zero_fills(table_arrays, capfd
 
 
 def test_table_with_zeroed_rows_keeps_fast_path_elsewhere(oracle_table, table_arrays):
-    """The reference zero-fills radii a frame does not cover.  Frames holding such rows fail the operand-range check of the
-    branch-free arithmetic; only sets that blend one of THOSE frames take the plain-intrinsic path, and either way the
-    values equal the oracle's."""
+    """The reference zero-fills radii a frame does not cover.  Exact zeros in the branches pass the operand-range check of the
+    branch-free arithmetic (a zero numerator is exact in every sequence; what the blend makes of a zero next to its neighbours
+    is checked per set on the blended frame), tiny non-zero values do not: only sets that blend one of THOSE frames take the
+    plain-intrinsic path, and either way the values equal the oracle's."""
     tab = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in table_arrays.items()}
     n_mu = tab["n_mu"]
     for f in (3 * n_mu + 5, 3 * n_mu + 6, 17 * n_mu + 11):
@@ -575,7 +576,19 @@ def test_table_with_zeroed_rows_keeps_fast_path_elsewhere(oracle_table, table_ar
         got = gt.eval_batch("kline5", p, E, precision="f32")
         want = ot.eval_batch("kline5", p, E, precision="f32", threads=os.cpu_count() or 1)["out"]
         assert np.array_equal(got, want, equal_nan=True)
-        assert "fast_frames=597/600" in gt.last_launch_info()
+        assert "fast_frames=600/600" in gt.last_launch_info()
+    finally:
+        gt.close()
+    # tiny non-zero branch values (below 2^-20) still take a frame out of the branch-free arithmetic; same values either way
+    tab["upper"][17 * n_mu + 11, :4] = 1e-9
+    tab["lower"][3 * n_mu + 5, 2:4] = 3e-8
+    gt = klp.Table.from_arrays(tab, 0)
+    ot = orc.OracleTable(tab)
+    try:
+        got = gt.eval_batch("kline5", p, E, precision="f32")
+        want = ot.eval_batch("kline5", p, E, precision="f32", threads=os.cpu_count() or 1)["out"]
+        assert np.array_equal(got, want, equal_nan=True)
+        assert "fast_frames=598/600" in gt.last_launch_info()
     finally:
         gt.close()
 

@@ -164,6 +164,9 @@ int klp_get_timing(klp_table* t, double* ms4, long* launches4);
  * sequences of klp_kernels.cuh when the operand-range checks pass (default), 0 = always use the
  * plain IEEE intrinsics; both give the same results). */
 int klp_set_option(klp_table* t, const char* key, long value);
+/* The staging chunks klp_eval_batch uses for B sets of n_flux bins with the given "stage_mb" / "stage_tail" (sizes[cap]); returns
+ * their number, -1 on bad arguments.  Host logic only: needs no device. */
+int klp_stage_chunk_plan(long B, int n_flux, long stage_mb, long stage_tail, long* sizes, int cap);
 
 /* What the most recent quadrature launch of this table was: "k_quad<float, 1024, 1> splits=1 ring=0 fast_frames=600/600"
  * (template instantiation = element type, CTA threads, blended frame in shared memory; CTAs per set; deposit-ring mode; how

@@ -86,6 +86,7 @@ def load_library():
     L.klp_group_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.klp_group_last_gather_ops.argtypes = [vp]
     L.klp_group_chunk_plan.argtypes = [C.c_long, C.c_long, C.c_long, C.POINTER(C.c_long), C.c_int]
+    L.klp_stage_chunk_plan.argtypes = [C.c_long, C.c_int, C.c_long, C.c_long, C.POINTER(C.c_long), C.c_int]
     sig = [dp, C.c_int, dp, C.c_int, dp, dp, C.c_char_p]
     for name in MODELS:
         fn = getattr(L, name)
@@ -319,6 +320,15 @@ def group_chunk_plan(B_local: int, gather_chunk: int = 131072, gather_tail: int 
     n = load_library().klp_group_chunk_plan(int(B_local), int(gather_chunk), int(gather_tail), buf, 4096)
     if n < 0:
         raise KlpError("klp_group_chunk_plan: bad arguments")
+    return [int(buf[i]) for i in range(n)]
+
+
+def stage_chunk_plan(B: int, n_flux: int, stage_mb: int = 256, stage_tail: int = 4096):
+    """Staging chunks of the host-buffer pipeline (klp_eval_batch): full pinned slots, then a short final chunk."""
+    buf = (C.c_long * 8192)()
+    n = load_library().klp_stage_chunk_plan(int(B), int(n_flux), int(stage_mb), int(stage_tail), buf, 8192)
+    if n < 0:
+        raise KlpError("klp_stage_chunk_plan: bad arguments")
     return [int(buf[i]) for i in range(n)]
 
 

@@ -567,6 +567,26 @@ int ensure_streams(klp_table* t) {
 
 // Host-buffer batch: chunked, double-buffered through pinned memory; H2D, compute and D2H run on
 // three streams so copies overlap the kernels.
+// Staging chunks of the host-buffer pipeline for B sets of n_flux bins: full slots of stage_mb megabytes of output (at least 16
+// and at most 65535 sets: very wide grids get fewer sets per slot, not more pinned memory), then a SHORT final chunk.  The
+// copy-out of the last chunk (D2H + the copy from the pinned slot into the caller's buffer: ~15 ms for a 128 MB slot) overlaps
+// nothing, so it is cut to stage_tail sets, at most a quarter slot (default 4096: ~4 ms exposed, and its ~30 ms of kernels cover
+// the copy-out of the chunk before it; measured on 1e5 kline5 sets: 128 MB slots 133.0 k spectra/s, 256 MB slots without the
+// short chunk 127.9 k, with it 134.5 k).  Host logic only (klp_stage_chunk_plan exposes it to the CPU tests).
+std::vector<long long> stage_chunks(long long B, int n_flux, long long stage_mb, long long stage_tail) {
+    long long hc = (stage_mb << 20) / ((long long)n_flux * 8);
+    hc = std::max<long long>(16, std::min<long long>(hc, 65535));
+    hc = std::min(hc, B);
+    long long tail = std::min<long long>(stage_tail, hc / 4);
+    if (tail < 1 || B <= hc + tail) tail = 0;
+    std::vector<long long> cuts;
+    long long off = 0;
+    const long long body = B - tail;
+    while (off < body) { const long long nb = std::min(hc, body - off); cuts.push_back(nb); off += nb; }
+    if (tail > 0) cuts.push_back(tail);
+    return cuts;
+}
+
 int eval_host(klp_table* t, int model, int precision, long long B, const double* params, const double* energy,
               int n_flux, const double* spectrum, int per_set, double* out, const EvalExtra& ex, double* lims_out) {
     if (!t) return fail(KLP_ERR_ARG, "null table");
@@ -600,9 +620,8 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
     // that read the grid / spectrum are enqueued on the same stream)
     // staging chunk: t->stage_mb of output per slot (two slots; default 256 MB).  Larger chunks amortise the idle tail of
     // every k_quad launch, smaller ones shorten the last, un-overlapped copy-out.
-    long long hc = ((long long)t->stage_mb << 20) / ((long long)n_flux * 8);
-    hc = std::max<long long>(16, std::min<long long>(hc, 65535));   // (very wide grids: fewer sets per slot, not more pinned memory)
-    hc = std::min(hc, B);
+    const std::vector<long long> cuts = stage_chunks(B, n_flux, t->stage_mb, t->stage_tail);
+    const long long hc = *std::max_element(cuts.begin(), cuts.end());   // sets per staging slot
     const size_t out_bytes = sizeof(double) * (size_t)hc * n_flux + 16;   // (+16: the radial-grid end points of a legacy call ride behind the spectra)
     const size_t par_bytes = sizeof(double) * (size_t)hc * P;
     for (int k = 0; k < 2; ++k) {
@@ -611,18 +630,6 @@ int eval_host(klp_table* t, int model, int precision, long long B, const double*
             return rc;
         if (conv && per_set)
             if ((rc = t->d_spec_slot[k].ensure(out_bytes)) || (rc = t->h_spec_slot[k].ensure(out_bytes))) return rc;
-    }
-    // Chunk sizes: full slots, then a SHORT final chunk.  The copy-out of the last chunk (D2H + the copy from the pinned slot
-    // into the caller's buffer: ~15 ms for a 128 MB slot) overlaps nothing, so the last chunk is cut to stage_tail sets
-    // (default 4096: ~4 ms exposed, and its ~30 ms of kernels cover the copy-out of the chunk before it; measured on 1e5 kline5 sets: 128 MB slots 133.0 k spectra/s, 256 MB slots without the short chunk 127.9 k, with it 134.5 k).
-    std::vector<long long> cuts;
-    {
-        long long tail = std::min<long long>(t->stage_tail, hc / 4);
-        if (tail < 1 || B <= hc + tail) tail = 0;
-        long long off = 0;
-        const long long body = B - tail;
-        while (off < body) { const long long nb = std::min(hc, body - off); cuts.push_back(nb); off += nb; }
-        if (tail > 0) cuts.push_back(tail);
     }
     const long long n_chunks = (long long)cuts.size();
     if ((rc = t->h_lims.ensure(16))) return rc;
@@ -1284,6 +1291,15 @@ int klp_get_phase_times(klp_table* t, double* us9) {
     KLP_CUDA(cudaMemcpy(h, t->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 10; ++k) us9[k] = h[k] ? (double)(h[k] - h[0]) * 1e-3 : -1.0;
     return KLP_OK;
+}
+
+// The staging chunks klp_eval_batch would use (sizes[cap]); returns their number, -1 on bad arguments.  No device needed.
+int klp_stage_chunk_plan(long B, int n_flux, long stage_mb, long stage_tail, long* sizes, int cap) {
+    if (B < 1 || n_flux < 1 || stage_mb < 1 || stage_tail < 0 || !sizes || cap < 1) return -1;
+    const std::vector<long long> cuts = stage_chunks(B, n_flux, stage_mb, stage_tail);
+    if ((int)cuts.size() > cap) return -1;
+    for (size_t i = 0; i < cuts.size(); ++i) sizes[i] = (long)cuts[i];
+    return (int)cuts.size();
 }
 
 int klp_set_option(klp_table* t, const char* key, long value) {

@@ -317,3 +317,23 @@ def test_one_correction_division_is_correctly_rounded(tmp_path):
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([str(exe), "quick"], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.startswith("bad=0 "), run.stdout
+
+
+def test_stage_chunk_plan():
+    """Host-buffer pipeline: full pinned slots, then a short final chunk (its copy-out overlaps nothing); small batches are one chunk
+    = one stream, one synchronisation (the XSPEC call pattern)."""
+    from lineprofiles_b200.api import stage_chunk_plan as plan
+    per_slot = (256 << 20) // 8000                       # 1000 bins: 33554 sets per 256 MB slot
+    assert plan(100000, 1000) == [per_slot, per_slot, 100000 - 2 * per_slot - 4096, 4096]
+    assert plan(100000, 1000, 128, 0) == [16777] * 5 + [100000 - 5 * 16777]
+    assert plan(1, 1000) == [1] and plan(per_slot, 1000) == [per_slot]            # one chunk
+    assert plan(per_slot + 4096, 1000) == [per_slot, 4096]                        # no tail when it would be the whole second chunk
+    assert plan(per_slot + 4097, 1000) == [per_slot, 1, 4096]
+    assert plan(700, 1000, 1, 4096) == [131] * 5 + [13, 32]                       # the tail is at most a quarter slot
+    assert plan(700, 1000, 1, 7) == [131] * 5 + [38, 7]
+    assert plan(100, 10 ** 6, 1) == [16] * 5 + [16, 4]                            # very wide grids: at least 16 sets per slot
+    assert plan(10 ** 6, 4, 4096) == [65535] * 15 + [10 ** 6 - 15 * 65535 - 4096, 4096]   # at most 65535 sets per slot
+    for B in (1, 17, 4097, 65536, 123457):
+        for n in (1, 1000, 4096):
+            p = plan(B, n)
+            assert sum(p) == B and all(c > 0 for c in p) and max(p) == p[0]
